@@ -1,0 +1,459 @@
+// Batch-norm statistics / apply / backward for NHWC bf16 activations: HBM-bound, 128-bit vectorised,
+// deterministic two-level reductions (per-block partials -> finalize), ReLU/ReLU6 and the residual add
+// fused.  Replaces nn.BatchNorm2d (+ nn.ReLU, + `out += residual`) of the reference
+// (models/resnet.py:88-91,115-116,128-134,162-163; models/mobilenet_v2.py:50-63) in train and eval.
+//
+// Thread mapping shared by all kernels: a block owns a contiguous range of rows (pixels); thread t is
+// (row_in_iter = t / cv, vec = t % cv) with cv = C/8 channel vectors, so every iteration of a block
+// touches one contiguous span of memory and per-channel coefficients are loaded once per thread.
+#include "common.cuh"
+#include "host.h"
+
+namespace b200 {
+
+constexpr int kBnThreads = 256;
+constexpr int kBnMaxBlocks = 1184;  // 8 per SM on 148 SMs
+
+struct RowMap {
+  int cv, rows_per_iter, active;
+};
+static inline RowMap make_rowmap(int C) {
+  RowMap m;
+  m.cv = C / 8;
+  m.rows_per_iter = kBnThreads / m.cv;
+  m.active = m.rows_per_iter * m.cv;
+  return m;
+}
+static inline int bn_blocks(long long M, const RowMap& rm) {
+  long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
+  long long want = (iters + 3) / 4;  // >= 4 iterations per block
+  if (want < 1) want = 1;
+  if (want > kBnMaxBlocks) want = kBnMaxBlocks;
+  return (int)want;
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ float act_mask(float y, int act) {
+  if (act == B200_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == B200_ACT_RELU6) return (y > 0.f && y < 6.f) ? 1.f : 0.f;
+  return 1.f;
+}
+
+// block-level reduction of 16 per-thread values over the rows_per_iter threads sharing a channel vector;
+// writes partial[block][stat(2)][C]
+__device__ __forceinline__ void block_reduce_write(float (&acc)[16], int cv, int rows_per_iter, int C,
+                                                   float* partial_blk) {
+  __shared__ float red[kBnThreads][17];
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) red[t][i] = acc[i];
+  __syncthreads();
+  for (int o = t; o < 2 * C; o += kBnThreads) {
+    const int stat = o / C;
+    const int c = o - stat * C;
+    const int v = c >> 3, e = c & 7;
+    float s = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r) s += red[r * cv + v][stat * 8 + e];
+    partial_blk[o] = s;
+  }
+}
+
+// ---- forward statistics -------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads) bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ z,
+                                                                      long long M, int C, int cv,
+                                                                      int rows_per_iter, float* __restrict__ partial) {
+  const int t = threadIdx.x;
+  const bool active = t < rows_per_iter * cv;
+  const int r0 = t / cv, v = t - r0 * cv;
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long row_begin = blockIdx.x * rows_per_block;
+  const long long row_end = min(M, row_begin + rows_per_block);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  if (active) {
+    long long r = row_begin + r0;
+    for (; r + 3LL * rows_per_iter < row_end; r += 4LL * rows_per_iter) {
+      float f[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(z + (r + (long long)u * rows_per_iter) * C + v * 8, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] += f[u][i]; acc[8 + i] += f[u][i] * f[u][i]; }
+    }
+    for (; r < row_end; r += rows_per_iter) {
+      float f[8];
+      load8(z + r * C + v * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i] += f[i]; acc[8 + i] += f[i] * f[i]; }
+    }
+  }
+  block_reduce_write(acc, cv, rows_per_iter, C, partial + (long long)blockIdx.x * 2 * C);
+}
+
+// second-level reduction: 16 channels x 16 slices of the partial blocks per CTA, doubles across slices
+__device__ __forceinline__ bool reduce_partials16(const float* __restrict__ partial, int nblocks, int C, int& c_out,
+                                                  double& s1_out, double& s2_out) {
+  __shared__ double sh[2][16][17];
+  const int cl = threadIdx.x & 15, sl = threadIdx.x >> 4;
+  const int c = blockIdx.x * 16 + cl;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C) {
+    for (int b = sl; b < nblocks; b += 16) {
+      s1 += (double)partial[(long long)b * 2 * C + c];
+      s2 += (double)partial[(long long)b * 2 * C + C + c];
+    }
+  }
+  sh[0][sl][cl] = s1;
+  sh[1][sl][cl] = s2;
+  __syncthreads();
+  if (sl != 0 || c >= C) return false;
+  s1 = 0.0; s2 = 0.0;
+  for (int i = 0; i < 16; ++i) { s1 += sh[0][i][cl]; s2 += sh[1][i][cl]; }
+  c_out = c; s1_out = s1; s2_out = s2;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ partial, int nblocks,
+                                         long long M, int C,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                         float momentum, float* running_mean, float* running_var,
+                                         long long* num_batches_tracked, float* mean, float* invstd, float* scale,
+                                         float* shift) {
+  int c; double s1, s2;
+  if (!reduce_partials16(partial, nblocks, C, c, s1, s2)) return;
+  const double mu = s1 / (double)M;
+  double var = s2 / (double)M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float istd = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)mu;
+  invstd[c] = istd;
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  const float sc = g * istd;
+  scale[c] = sc;
+  shift[c] = bt - (float)mu * sc;
+  if (running_mean != nullptr && running_var != nullptr) {
+    float f = momentum;
+    if (momentum < 0.f) {  // cumulative moving average (momentum=None), factor = 1/(num_batches_tracked+1)
+      const long long nbt = num_batches_tracked ? *num_batches_tracked : 0;
+      f = 1.f / (float)(nbt + 1);
+    }
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (1.f - f) * running_mean[c] + f * (float)mu;
+    running_var[c] = (1.f - f) * running_var[c] + f * (float)unbiased;
+  }
+}
+__global__ void bn_bump_counter_kernel(long long* num_batches_tracked) { *num_batches_tracked += 1; }
+
+__global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv,
+                                      float eps, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float istd = rsqrtf(rv[c] + eps);
+  const float sc = (gamma ? gamma[c] : 1.f) * istd;
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+// ---- forward apply ------------------------------------------------------------------------------
+template <int MODE>  // 0: none, 1: + residual, 2: + (z2*scale2+shift2)
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long M, int C,
+                                                              int cv, int rows_per_iter,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const __nv_bfloat16* __restrict__ res,
+                                                              const float* __restrict__ scale2,
+                                                              const float* __restrict__ shift2, int act,
+                                                              __nv_bfloat16* __restrict__ y) {
+  const int t = threadIdx.x;
+  if (t >= rows_per_iter * cv) return;
+  const int r0 = t / cv, v = t - r0 * cv;
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long row_begin = blockIdx.x * rows_per_block;
+  const long long row_end = min(M, row_begin + rows_per_block);
+  float sc[8], sh[8], sc2[8], sh2[8];
+  loadf8(scale + v * 8, sc);
+  loadf8(shift + v * 8, sh);
+  if (MODE == 2) { loadf8(scale2 + v * 8, sc2); loadf8(shift2 + v * 8, sh2); }
+  for (long long r = row_begin + r0; r < row_end; r += 2LL * rows_per_iter) {
+    const long long ra = r, rb = r + rows_per_iter;
+    const bool hb = rb < row_end;
+    float fa[8], fb[8], ga[8], gb[8];
+    load8(z + ra * C + v * 8, fa);
+    if (hb) load8(z + rb * C + v * 8, fb);
+    if (MODE != 0) {
+      load8(res + ra * C + v * 8, ga);
+      if (hb) load8(res + rb * C + v * 8, gb);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = fa[i] * sc[i] + sh[i];
+      float b = fb[i] * sc[i] + sh[i];
+      if (MODE == 1) { a += ga[i]; b += gb[i]; }
+      if (MODE == 2) { a += ga[i] * sc2[i] + sh2[i]; b += gb[i] * sc2[i] + sh2[i]; }
+      if (act == B200_ACT_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+      if (act == B200_ACT_RELU6) { a = fminf(fmaxf(a, 0.f), 6.f); b = fminf(fmaxf(b, 0.f), 6.f); }
+      fa[i] = a; fb[i] = b;
+    }
+    store8(y + ra * C + v * 8, fa);
+    if (hb) store8(y + rb * C + v * 8, fb);
+  }
+}
+
+// ---- backward reduce: dbeta = sum g, dgamma = sum g * xhat, g = dy * act'(y) ---------------------
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                    const __nv_bfloat16* __restrict__ y,
+                                                                    const __nv_bfloat16* __restrict__ z, long long M,
+                                                                    int C, int cv, int rows_per_iter, int act,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ invstd,
+                                                                    float* __restrict__ partial) {
+  const int t = threadIdx.x;
+  const bool active = t < rows_per_iter * cv;
+  const int r0 = t / cv, v = t - r0 * cv;
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long row_begin = blockIdx.x * rows_per_block;
+  const long long row_end = min(M, row_begin + rows_per_block);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  if (active) {
+    float mu[8], is[8];
+    loadf8(mean + v * 8, mu);
+    loadf8(invstd + v * 8, is);
+    for (long long r = row_begin + r0; r < row_end; r += 2LL * rows_per_iter) {
+      const long long rb = r + rows_per_iter;
+      const bool hb = rb < row_end;
+      float da[8], db[8], za[8], zb[8], ya[8], yb[8];
+      load8(dy + r * C + v * 8, da);
+      load8(z + r * C + v * 8, za);
+      if (act != B200_ACT_NONE) load8(y + r * C + v * 8, ya);
+      if (hb) {
+        load8(dy + rb * C + v * 8, db);
+        load8(z + rb * C + v * 8, zb);
+        if (act != B200_ACT_NONE) load8(y + rb * C + v * 8, yb);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float g = da[i];
+        if (act != B200_ACT_NONE) g *= act_mask(ya[i], act);
+        acc[i] += g * (za[i] - mu[i]) * is[i];
+        acc[8 + i] += g;
+        if (hb) {
+          float g2 = db[i];
+          if (act != B200_ACT_NONE) g2 *= act_mask(yb[i], act);
+          acc[i] += g2 * (zb[i] - mu[i]) * is[i];
+          acc[8 + i] += g2;
+        }
+      }
+    }
+  }
+  block_reduce_write(acc, cv, rows_per_iter, C, partial + (long long)blockIdx.x * 2 * C);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                       float* sums, float* dgamma_acc, float* dbeta_acc) {
+  int c; double s1, s2;
+  if (!reduce_partials16(partial, nblocks, C, c, s1, s2)) return;
+  sums[c] = (float)s1;
+  sums[C + c] = (float)s2;
+  if (dgamma_acc) dgamma_acc[c] += (float)s1;
+  if (dbeta_acc) dbeta_acc[c] += (float)s2;
+}
+
+// ---- backward dx --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ y,
+                                                               const __nv_bfloat16* __restrict__ z, long long M, int C,
+                                                               int cv, int rows_per_iter, int act,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ sums,
+                                                               __nv_bfloat16* __restrict__ dz,
+                                                               __nv_bfloat16* __restrict__ g_out) {
+  const int t = threadIdx.x;
+  if (t >= rows_per_iter * cv) return;
+  const int r0 = t / cv, v = t - r0 * cv;
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long row_begin = blockIdx.x * rows_per_block;
+  const long long row_end = min(M, row_begin + rows_per_block);
+  // dz = A*g + B*z + Cc  with A = gamma*istd, B = -gamma*istd^2*dgamma/M, Cc = -A*dbeta/M - B*mean
+  float A[8], B[8], Cc[8];
+  {
+    float mu[8], is[8], ga[8], dg[8], dbt[8];
+    loadf8(mean + v * 8, mu);
+    loadf8(invstd + v * 8, is);
+    if (gamma) loadf8(gamma + v * 8, ga);
+    loadf8(sums + v * 8, dg);
+    loadf8(sums + C + v * 8, dbt);
+    const float invM = 1.f / (float)M;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gm = gamma ? ga[i] : 1.f;
+      A[i] = gm * is[i];
+      B[i] = -gm * is[i] * is[i] * dg[i] * invM;
+      Cc[i] = -A[i] * dbt[i] * invM - B[i] * mu[i];
+    }
+  }
+  for (long long r = row_begin + r0; r < row_end; r += 2LL * rows_per_iter) {
+    const long long rb = r + rows_per_iter;
+    const bool hb = rb < row_end;
+    float da[8], db[8], za[8], zb[8], ya[8], yb[8];
+    load8(dy + r * C + v * 8, da);
+    load8(z + r * C + v * 8, za);
+    if (act != B200_ACT_NONE) load8(y + r * C + v * 8, ya);
+    if (hb) {
+      load8(dy + rb * C + v * 8, db);
+      load8(z + rb * C + v * 8, zb);
+      if (act != B200_ACT_NONE) load8(y + rb * C + v * 8, yb);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float g = da[i];
+      if (act != B200_ACT_NONE) g *= act_mask(ya[i], act);
+      da[i] = g;
+      za[i] = A[i] * g + B[i] * za[i] + Cc[i];
+      if (hb) {
+        float g2 = db[i];
+        if (act != B200_ACT_NONE) g2 *= act_mask(yb[i], act);
+        db[i] = g2;
+        zb[i] = A[i] * g2 + B[i] * zb[i] + Cc[i];
+      }
+    }
+    store8(dz + r * C + v * 8, za);
+    if (g_out) store8(g_out + r * C + v * 8, da);
+    if (hb) {
+      store8(dz + rb * C + v * 8, zb);
+      if (g_out) store8(g_out + rb * C + v * 8, db);
+    }
+  }
+}
+
+static int check_c(int C, const char* who) {
+  B200_REQUIRE(C > 0 && C % 8 == 0 && C <= 2048, B200_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 8 and <= 2048",
+               who, C);
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" size_t b200_bn_workspace_floats(int C) { return (size_t)kBnMaxBlocks * 2 * (size_t)(C > 0 ? C : 0); }
+
+extern "C" int b200_bn_stats(const void* z, long long M, int C, const float* gamma, const float* beta, float eps,
+                             float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
+                             float* invstd, float* scale, float* shift, float* workspace, b200_stream_t stream_) {
+  int rc = check_c(C, "bn_stats");
+  if (rc) return rc;
+  B200_REQUIRE(z && mean && invstd && scale && shift && workspace && M > 0, B200_ERR_INVALID, "bn_stats: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const RowMap rm = make_rowmap(C);
+  const int blocks = bn_blocks(M, rm);
+  bn_stats_partial_kernel<<<blocks, kBnThreads, 0, stream>>>((const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter,
+                                                            workspace);
+  B200_CHECK_LAUNCH("bn_stats_partial_kernel");
+  bn_stats_finalize_kernel<<<(C + 15) / 16, 256, 0, stream>>>(workspace, blocks, M, C, gamma, beta, eps, momentum,
+                                                               running_mean, running_var, nbt, mean, invstd, scale,
+                                                               shift);
+  B200_CHECK_LAUNCH("bn_stats_finalize_kernel");
+  if (nbt != nullptr && running_mean != nullptr) {
+    bn_bump_counter_kernel<<<1, 1, 0, stream>>>(nbt);
+    B200_CHECK_LAUNCH("bn_bump_counter_kernel");
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                                   const float* running_var, float eps, float* scale, float* shift,
+                                   b200_stream_t stream_) {
+  B200_REQUIRE(C > 0 && running_mean && running_var && scale && shift, B200_ERR_INVALID, "bn_eval_coeffs: bad argument");
+  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(C, gamma, beta, running_mean, running_var,
+                                                                         eps, scale, shift);
+  B200_CHECK_LAUNCH("bn_eval_coeffs_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_apply(const void* z, long long M, int C, const float* scale, const float* shift,
+                             const void* residual, const void* z2, const float* scale2, const float* shift2, int act,
+                             void* y, b200_stream_t stream_) {
+  int rc = check_c(C, "bn_apply");
+  if (rc) return rc;
+  B200_REQUIRE(z && scale && shift && y && M > 0, B200_ERR_INVALID, "bn_apply: bad argument");
+  B200_REQUIRE(!(residual && z2), B200_ERR_INVALID, "bn_apply: residual and z2 are exclusive");
+  B200_REQUIRE(!z2 || (scale2 && shift2), B200_ERR_INVALID, "bn_apply: z2 needs scale2/shift2");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const RowMap rm = make_rowmap(C);
+  long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
+  long long blocks = (iters + 7) / 8;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 4 * kBnMaxBlocks) blocks = 4 * kBnMaxBlocks;
+  const __nv_bfloat16* zz = (const __nv_bfloat16*)z;
+  __nv_bfloat16* yy = (__nv_bfloat16*)y;
+  if (residual)
+    bn_apply_kernel<1><<<(int)blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
+                                                               (const __nv_bfloat16*)residual, nullptr, nullptr, act, yy);
+  else if (z2)
+    bn_apply_kernel<2><<<(int)blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
+                                                               (const __nv_bfloat16*)z2, scale2, shift2, act, yy);
+  else
+    bn_apply_kernel<0><<<(int)blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift, nullptr,
+                                                               nullptr, nullptr, act, yy);
+  B200_CHECK_LAUNCH("bn_apply_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const void* z, long long M, int C, int act,
+                                  const float* mean, const float* invstd, float* sums, float* dgamma_acc,
+                                  float* dbeta_acc, float* workspace, b200_stream_t stream_) {
+  int rc = check_c(C, "bn_bwd_reduce");
+  if (rc) return rc;
+  B200_REQUIRE(dy && z && mean && invstd && sums && workspace && M > 0, B200_ERR_INVALID, "bn_bwd_reduce: bad argument");
+  B200_REQUIRE(act == B200_ACT_NONE || y, B200_ERR_INVALID, "bn_bwd_reduce: activation mask needs y");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const RowMap rm = make_rowmap(C);
+  const int blocks = bn_blocks(M, rm);
+  bn_bwd_partial_kernel<<<blocks, kBnThreads, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+                                                          (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, act,
+                                                          mean, invstd, workspace);
+  B200_CHECK_LAUNCH("bn_bwd_partial_kernel");
+  bn_bwd_finalize_kernel<<<(C + 15) / 16, 256, 0, stream>>>(workspace, blocks, C, sums, dgamma_acc, dbeta_acc);
+  B200_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const void* z, long long M, int C, int act,
+                              const float* mean, const float* invstd, const float* gamma, const float* sums, void* dz,
+                              void* g_out, b200_stream_t stream_) {
+  int rc = check_c(C, "bn_bwd_dx");
+  if (rc) return rc;
+  B200_REQUIRE(dy && z && mean && invstd && sums && dz && M > 0, B200_ERR_INVALID, "bn_bwd_dx: bad argument");
+  B200_REQUIRE(act == B200_ACT_NONE || y, B200_ERR_INVALID, "bn_bwd_dx: activation mask needs y");
+  const RowMap rm = make_rowmap(C);
+  long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
+  long long blocks = (iters + 7) / 8;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 4 * kBnMaxBlocks) blocks = 4 * kBnMaxBlocks;
+  bn_bwd_dx_kernel<<<(int)blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, act,
+      mean, invstd, gamma, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);
+  B200_CHECK_LAUNCH("bn_bwd_dx_kernel");
+  return B200_OK;
+}

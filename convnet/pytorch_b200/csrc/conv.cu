@@ -1,0 +1,747 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a): fprop, dgrad, wgrad.
+//
+//   fprop : y[m, k]   = sum_{tap, c} x_im2col[m, tap, c] * w[k, tap, c]        (A K-major, B K-major)
+//   dgrad : dx[m, c]  = sum_{tap, k} dy_im2col[m, tap, k] * wt[c, tap, k]       (same kernel, tap table)
+//   wgrad : dw[k, tap, c] += sum_{pix} dy[pix, k] * x_im2col[pix, tap, c]       (A MN-major, B MN-major)
+//
+// Operand tiles are staged by TMA (im2col mode for the activation side, tiled mode for weights / dy)
+// into 32/64/128B-swizzled shared memory, consumed by single-thread-issued tcgen05.mma with fp32
+// accumulators in TMEM, drained by 4 epilogue warps with tcgen05.ld.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+//
+// Replaces cuDNN's convolution behind nn.Conv2d in the reference (models/resnet.py:75-78,126-132,
+// 226-227) and its autograd backward (trainer.py:162).
+#include "common.cuh"
+#include "host.h"
+
+namespace b200 {
+
+constexpr int kMaxStages = 8;
+constexpr int kMaxTaps = 32;
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr uint32_t kTmemCols = 512;
+
+struct TapEntry {
+  uint16_t off_w, off_h;  // im2col filter offsets (added to the base pixel)
+  uint16_t b_tap;         // which tap slice of the weight operand
+  uint16_t pad_;
+};
+
+struct IgemmParams {
+  int M_total;           // rows of the implicit GEMM = Nimg * I * J
+  int I, J;              // base-pixel grid per image
+  int trav;              // traversal stride of base pixels in the source tensor
+  int lower_w, lower_h;  // source coordinate of base pixel (0,0)
+  int N_total;           // GEMM N (channels produced)
+  int block_n, n_tiles, m_tiles;
+  int ck, c_chunks;      // channels per k-block, number of k-blocks per tap
+  int ntaps;
+  int num_stages;
+  uint32_t a_bytes, b_bytes, tx_bytes;
+  // output mapping: row m=(n,i,j) -> out pixel (n, i*os+oh0, j*os+ow0) of an [Nimg,OH,OW,ldo] tensor
+  int OH, OW, os, oh0, ow0;
+  int ldo;
+  int act, out_fp32;
+  void* out;
+  const void* res;
+  const float* bias;
+  TapEntry taps[kMaxTaps];
+};
+
+__device__ __forceinline__ void store_chunk16(const IgemmParams& p, const uint32_t (&v)[16], long long off,
+                                              int n0, bool row_ok) {
+  // v: 16 consecutive fp32 accumulators (as bits) for columns [n0, n0+16) of this thread's row
+  if (!row_ok) return;
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+  const bool full = (n0 + 16 <= p.N_total);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (n0 + i < p.N_total) f[i] += __ldg(p.bias + n0 + i);
+  }
+  if (p.res != nullptr) {
+    const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res) + off + n0;
+    if (full && ((p.ldo & 7) == 0)) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(r);
+      const uint4 r1 = *reinterpret_cast<const uint4*>(r + 8);
+      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float2 t = unpack_bf16x2(rr[i]);
+        f[2 * i] += t.x;
+        f[2 * i + 1] += t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (n0 + i < p.N_total) f[i] += __bfloat162float(r[i]);
+    }
+  }
+  if (p.act == B200_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+  } else if (p.act == B200_ACT_RELU6) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fminf(fmaxf(f[i], 0.f), 6.f);
+  }
+  if (p.out_fp32) {
+    float* o = reinterpret_cast<float*>(p.out) + off + n0;
+    if (full && ((p.ldo & 3) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (n0 + i < p.N_total) o[i] = f[i];
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off + n0;
+    if (full && ((p.ldo & 7) == 0)) {
+      uint4 a, b;
+      a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+      a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+      b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+      b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+      *reinterpret_cast<uint4*>(o) = a;
+      *reinterpret_cast<uint4*>(o + 8) = b;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (n0 + i < p.N_total) o[i] = __float2bfloat16(f[i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4);
+    mbar_init(&tmem_empty[1], 4);
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.ntaps * p.c_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int IJ = p.I * p.J;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int m0 = m_tile * kTileM;
+        const int img = m0 / IJ;
+        const int rem = m0 - img * IJ;
+        const int bi = rem / p.J;
+        const int bj = rem - bi * p.J;
+        const int base_w = bj * p.trav + p.lower_w;
+        const int base_h = bi * p.trav + p.lower_h;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const TapEntry te = p.taps[t];
+          for (int cc = 0; cc < p.c_chunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + p.a_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
+            tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cc * p.ck, base_w, base_h, img, te.off_w, te.off_h);
+            tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.ck, te.b_tap, n_tile * p.block_n);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n, 0, 0);
+      const uint32_t row_bytes = p.ck * 2;
+      const uint32_t lt = layout_type_for_row_bytes(row_bytes);
+      const uint32_t sbo = 8 * row_bytes;
+      const int ksteps = p.ck / 16;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1u;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, lt);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, lt);
+            umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int IJ = p.I * p.J;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1u;
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int m = m_tile * kTileM + q * 32 + lane;
+      const bool row_ok = m < p.M_total;
+      long long off = 0;
+      if (row_ok) {
+        const int img = m / IJ;
+        const int rem = m - img * IJ;
+        const int bi = rem / p.J;
+        const int bj = rem - bi * p.J;
+        off = ((static_cast<long long>(img) * p.OH + (bi * p.os + p.oh0)) * p.OW + (bj * p.os + p.ow0)) *
+              static_cast<long long>(p.ldo);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+      const int nbase = n_tile * p.block_n;
+      int c0 = 0;
+      for (; c0 + 32 <= p.block_n; c0 += 32) {
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr + c0, v0);
+        tmem_ld16(taddr + c0 + 16, v1);
+        tmem_ld_wait();
+        store_chunk16(p, v0, off, nbase + c0, row_ok && (nbase + c0 < p.N_total));
+        store_chunk16(p, v1, off, nbase + c0 + 16, row_ok && (nbase + c0 + 16 < p.N_total));
+      }
+      for (; c0 < p.block_n; c0 += 16) {
+        uint32_t v0[16];
+        tmem_ld16(taddr + c0, v0);
+        tmem_ld_wait();
+        store_chunk16(p, v0, off, nbase + c0, row_ok && (nbase + c0 < p.N_total));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: dw[k, tap, c] += sum_pix dy[pix, k] * x[pix @ tap, c]
+// A = dy tile, MN-major (rows of smem = pixels, 128/64/32B of k-channels); B = im2col(x) tile, MN-major.
+struct WgradParams {
+  int M_total;          // fwd output pixels N*P*Q
+  int P, Q;
+  int trav;             // conv stride
+  int lower_w, lower_h; // -pad
+  int K_out, C, taps_total;
+  int ckA, ckB;         // channels per smem box on the dy side / x side
+  int bk;               // pixels per stage
+  int c_chunks;         // ceil(C / ckB)
+  int total_boxes;      // taps * c_chunks
+  int boxes_per_cta;    // <= 512 / ckB and <= 8
+  int k_tiles, col_groups, splits;
+  int blocks_per_split, total_blocks;  // in units of bk pixels
+  int num_stages;
+  uint32_t boxA_bytes, boxB_bytes, stage_bytes;
+  float* dw;
+  TapEntry taps[kMaxTaps];
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+    prefetch_tmap(&tmDy);
+    prefetch_tmap(&tmX);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // work decomposition
+  const int tiles = p.k_tiles * p.col_groups;
+  const int split = blockIdx.x / tiles;
+  const int tile = blockIdx.x - split * tiles;
+  const int k_tile = tile % p.k_tiles;
+  const int cgroup = tile / p.k_tiles;
+  const int k0 = k_tile * kTileM;
+  const int box0 = cgroup * p.boxes_per_cta;
+  const int nboxes = min(p.boxes_per_cta, p.total_boxes - box0);
+  const int blk_begin = split * p.blocks_per_split;
+  const int blk_end = min(p.total_blocks, blk_begin + p.blocks_per_split);
+  const int nblk = blk_end - blk_begin;
+  const int nA = min(kTileM / p.ckA, (p.K_out - k0 + p.ckA - 1) / p.ckA);  // dy boxes actually loaded
+  const uint32_t a_region = (kTileM / p.ckA) * p.boxA_bytes;
+
+  if (nblk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int PQ = p.P * p.Q;
+        const uint32_t tx = nA * p.boxA_bytes + nboxes * p.boxB_bytes;
+        for (int b = blk_begin; b < blk_end; ++b) {
+          const int pix0 = b * p.bk;
+          const int img = pix0 / PQ;
+          const int rem = pix0 - img * PQ;
+          const int pi = rem / p.Q;
+          const int pj = rem - pi * p.Q;
+          const int base_w = pj * p.trav + p.lower_w;
+          const int base_h = pi * p.trav + p.lower_h;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * p.stage_bytes;
+          uint8_t* sb = sa + a_region;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          for (int a = 0; a < nA; ++a)
+            tma_load_2d(&tmDy, &full_bar[stage], sa + a * p.boxA_bytes, k0 + a * p.ckA, pix0);
+          for (int x = 0; x < nboxes; ++x) {
+            const int id = box0 + x;
+            const int t = id / p.c_chunks;
+            const int cc = id - t * p.c_chunks;
+            const TapEntry te = p.taps[t];
+            tma_load_im2col_4d(&tmX, &full_bar[stage], sb + x * p.boxB_bytes, cc * p.ckB, base_w, base_h, img,
+                               te.off_w, te.off_h);
+          }
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t ltA = layout_type_for_row_bytes(p.ckA * 2);
+        const uint32_t ltB = layout_type_for_row_bytes(p.ckB * 2);
+        const uint32_t sboA = 8 * p.ckA * 2, sboB = 8 * p.ckB * 2;
+        const int boxes_per_mma = min(8, 256 / p.ckB);
+        const int ksteps = p.bk / 16;
+        for (int b = 0; b < nblk; ++b) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + a_region;
+          for (int g0 = 0; g0 < nboxes; g0 += boxes_per_mma) {
+            const int nb = min(boxes_per_mma, nboxes - g0);
+            const uint32_t idesc = make_idesc_bf16(kTileM, nb * p.ckB, 1, 1);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * 16 * p.ckA * 2, p.boxA_bytes, sboA, ltA);
+              const uint64_t db =
+                  make_smem_desc(b_addr + g0 * p.boxB_bytes + k * 16 * p.ckB * 2, p.boxB_bytes, sboB, ltB);
+              umma_bf16(tmem_base + g0 * p.ckB, da, db, idesc, (b | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (b == nblk - 1) umma_commit(&acc_bar);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else {
+      const int q = warp & 3;
+      const int k = k0 + q * 32 + lane;
+      const bool row_ok = k < p.K_out;
+      mbar_wait(&acc_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      for (int x = 0; x < nboxes; ++x) {
+        const int id = box0 + x;
+        const int t = id / p.c_chunks;
+        const int cc = id - t * p.c_chunks;
+        const int tap = p.taps[t].b_tap;
+        const int cbase = cc * p.ckB;
+        float* dst = p.dw + (static_cast<long long>(k) * p.taps_total + tap) * p.C + cbase;
+        for (int c0 = 0; c0 < p.ckB; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + x * p.ckB + c0, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            if (cbase + c0 + 16 <= p.C && (p.C & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                red_add_v4(dst + c0 + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (cbase + c0 + i < p.C) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+static int pick_ck(int channels) { return channels <= 16 ? 16 : (channels <= 32 ? 32 : 64); }
+
+static int encode_im2col(CUtensorMap* tm, const void* base, int Nimg, int H, int W, int C, int ck, int pixels,
+                         int lower_w, int lower_h, int upper_w, int upper_h, int trav) {
+  EncodeIm2colFn fn = encode_im2col_fn();
+  B200_REQUIRE(fn != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeIm2col entry point unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)trav, (cuuint32_t)trav, 1};
+  B200_REQUIRE(lower_w >= -128 && lower_w <= 127 && lower_h >= -128 && lower_h <= 127 && upper_w >= -128 &&
+                   upper_w <= 127 && upper_h >= -128 && upper_h <= 127,
+               B200_ERR_UNSUPPORTED, "im2col corner offsets out of the TMA range");
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+                  (cuuint32_t)ck, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_for_row_bytes(ck * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA,
+               "cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d ck=%d pix=%d lower=(%d,%d) upper=(%d,%d) trav=%d",
+               (int)r, Nimg, H, W, C, ck, pixels, lower_w, lower_h, upper_w, upper_h, trav);
+  // Driver quirk for small tensors (as worked around by CUTLASS' im2col descriptor builder):
+  // for tensors below 128 KiB, bit 21 of the second descriptor word must be cleared on drivers <= 13.1.
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (size_t)Nimg * H * W * C * 2 < 131072) {
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  }
+  return B200_OK;
+}
+
+static int encode_tiled3(CUtensorMap* tm, const void* base, int d0, int d1, int d2, int b0, int b1, int b2) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  B200_REQUIRE(fn != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)d0 * 2, (cuuint64_t)d0 * d1 * 2};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(b0 * 2),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) dims=(%d,%d,%d) box=(%d,%d,%d)",
+               (int)r, d0, d1, d2, b0, b1, b2);
+  return B200_OK;
+}
+
+static int encode_tiled2(CUtensorMap* tm, const void* base, int d0, long long d1, int b0, int b1) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  B200_REQUIRE(fn != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+  cuuint64_t strides[1] = {(cuuint64_t)d0 * 2};
+  cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(b0 * 2),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed (%d) dims=(%d,%lld) box=(%d,%d)",
+               (int)r, d0, d1, b0, b1);
+  return B200_OK;
+}
+
+static const int kSmemBudget = 200 * 1024;
+
+static int set_smem_attr(const void* fn, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  B200_REQUIRE(e == cudaSuccess, B200_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
+  return B200_OK;
+}
+
+// One implicit-GEMM launch.  src: [Nimg, SH, SW, SC] bf16 (im2col source); wmat: [Nout][wtaps][SC] bf16.
+struct IgemmLaunch {
+  const void* src; int Nimg, SH, SW, SC;
+  const void* wmat; int Nout, wtaps;
+  int I, J, trav, lower_w, lower_h;
+  int ntaps; TapEntry taps[kMaxTaps];
+  void* out; int OH, OW, os, oh0, ow0, ldo;
+  const void* res; const float* bias; int act, out_fp32;
+};
+
+static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
+  B200_REQUIRE(L.SC % 8 == 0, B200_ERR_UNSUPPORTED, "igemm: source channels (%d) must be a multiple of 8", L.SC);
+  B200_REQUIRE(L.ntaps >= 1 && L.ntaps <= kMaxTaps, B200_ERR_UNSUPPORTED, "igemm: %d taps unsupported", L.ntaps);
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M_total = L.Nimg * L.I * L.J;
+  B200_REQUIRE(p.M_total > 0, B200_ERR_INVALID, "igemm: empty problem");
+  p.I = L.I; p.J = L.J; p.trav = L.trav; p.lower_w = L.lower_w; p.lower_h = L.lower_h;
+  p.N_total = L.Nout;
+  p.n_tiles = (L.Nout + 255) / 256;
+  p.block_n = (((L.Nout + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
+  p.m_tiles = (p.M_total + kTileM - 1) / kTileM;
+  p.ck = pick_ck(L.SC);
+  p.c_chunks = (L.SC + p.ck - 1) / p.ck;
+  p.ntaps = L.ntaps;
+  p.a_bytes = kTileM * p.ck * 2;
+  p.b_bytes = p.block_n * p.ck * 2;
+  p.tx_bytes = p.a_bytes + p.b_bytes;
+  // keep every stage 1024B aligned (128B-swizzle atoms are 1024B)
+  uint32_t stage = p.a_bytes + p.b_bytes;
+  if (stage % 1024) { p.b_bytes += 1024 - stage % 1024; stage = p.a_bytes + p.b_bytes; }
+  p.num_stages = kSmemBudget / (int)stage;
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  if (p.num_stages < 2) p.num_stages = 2;
+  p.OH = L.OH; p.OW = L.OW; p.os = L.os; p.oh0 = L.oh0; p.ow0 = L.ow0; p.ldo = L.ldo;
+  p.act = L.act; p.out_fp32 = L.out_fp32; p.out = L.out; p.res = L.res; p.bias = L.bias;
+  for (int t = 0; t < L.ntaps; ++t) p.taps[t] = L.taps[t];
+
+  // bounding box of base pixels: [lower, lower + (I-1)*trav] in a source of extent SH x SW
+  const int upper_w = L.lower_w + (L.J - 1) * L.trav + 1 - L.SW;
+  const int upper_h = L.lower_h + (L.I - 1) * L.trav + 1 - L.SH;
+  CUtensorMap tmA, tmB;
+  int rc = encode_im2col(&tmA, L.src, L.Nimg, L.SH, L.SW, L.SC, p.ck, kTileM, L.lower_w, L.lower_h, upper_w,
+                         upper_h, L.trav);
+  if (rc) return rc;
+  rc = encode_tiled3(&tmB, L.wmat, L.SC, L.wtaps, L.Nout, p.ck, 1, p.block_n);
+  if (rc) return rc;
+
+  const int smem_bytes = p.num_stages * (int)stage + 1024;
+  rc = set_smem_attr((const void*)conv_igemm_kernel, smem_bytes);
+  if (rc) return rc;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH("conv_igemm_kernel");
+  return B200_OK;
+}
+
+static int check_desc(const b200_conv_desc* d) {
+  B200_REQUIRE(d != nullptr, B200_ERR_INVALID, "conv: null descriptor");
+  B200_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0 && d->P > 0 &&
+                   d->Q > 0 && d->stride >= 1 && d->stride <= 8,
+               B200_ERR_INVALID, "conv: bad descriptor N=%d H=%d W=%d C=%d K=%d R=%d S=%d P=%d Q=%d stride=%d", d->N,
+               d->H, d->W, d->C, d->K, d->R, d->S, d->P, d->Q, d->stride);
+  B200_REQUIRE(d->R * d->S <= kMaxTaps, B200_ERR_UNSUPPORTED, "conv: %dx%d filter exceeds %d taps", d->R, d->S,
+               kMaxTaps);
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const void* w, void* y,
+                               const b200_epilogue* ep, b200_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  B200_REQUIRE(x && w && y, B200_ERR_INVALID, "conv_fprop: null pointer");
+  B200_REQUIRE(d->C % 8 == 0, B200_ERR_UNSUPPORTED, "conv_fprop: C=%d must be a multiple of 8 (pad the input)", d->C);
+  IgemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.src = x; L.Nimg = d->N; L.SH = d->H; L.SW = d->W; L.SC = d->C;
+  L.wmat = w; L.Nout = d->K; L.wtaps = d->R * d->S;
+  L.I = d->P; L.J = d->Q; L.trav = d->stride; L.lower_w = -d->pad_w; L.lower_h = -d->pad_h;
+  L.ntaps = d->R * d->S;
+  for (int r = 0; r < d->R; ++r)
+    for (int s = 0; s < d->S; ++s) {
+      TapEntry& t = L.taps[r * d->S + s];
+      t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.b_tap = (uint16_t)(r * d->S + s); t.pad_ = 0;
+    }
+  L.out = y; L.OH = d->P; L.OW = d->Q; L.os = 1; L.oh0 = 0; L.ow0 = 0; L.ldo = d->K;
+  L.res = ep ? ep->residual : nullptr;
+  L.bias = ep ? ep->bias : nullptr;
+  L.act = ep ? ep->act : 0;
+  L.out_fp32 = ep ? ep->out_fp32 : 0;
+  return launch_igemm(L, (cudaStream_t)stream);
+}
+
+extern "C" int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* wt, void* dx,
+                               const void* residual, b200_stream_t stream_) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_REQUIRE(dy && wt && dx, B200_ERR_INVALID, "conv_dgrad: null pointer");
+  B200_REQUIRE(d->K % 8 == 0, B200_ERR_UNSUPPORTED, "conv_dgrad: K=%d must be a multiple of 8", d->K);
+  const int st = d->stride;
+  B200_REQUIRE(st == 1 || st == 2, B200_ERR_UNSUPPORTED, "conv_dgrad: stride %d unsupported", st);
+  // dx[h,w] = sum_{r,s : (h+pad-r) % st == 0} dy[(h+pad-r)/st, (w+pad-s)/st] * w[r,s]
+  // one launch per residue class (h % st, w % st); each class is a stride-1 correlation over dy.
+  bool any_empty = false;
+  for (int ph = 0; ph < st; ++ph)
+    for (int pw = 0; pw < st; ++pw) {
+      int nr = 0, ns = 0;
+      for (int r = 0; r < d->R; ++r) if (((ph + d->pad_h - r) % st + st) % st == 0) ++nr;
+      for (int s = 0; s < d->S; ++s) if (((pw + d->pad_w - s) % st + st) % st == 0) ++ns;
+      if (nr * ns == 0 && (d->H - ph + st - 1) / st > 0 && (d->W - pw + st - 1) / st > 0) any_empty = true;
+    }
+  if (any_empty) {
+    B200_REQUIRE(residual == nullptr, B200_ERR_UNSUPPORTED,
+                 "conv_dgrad: residual add with an empty stride class is unsupported");
+    cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->C * 2, stream);
+    B200_REQUIRE(e == cudaSuccess, B200_ERR_CUDA, "conv_dgrad: memset failed: %s", cudaGetErrorString(e));
+    count_launch();
+  }
+  for (int ph = 0; ph < st; ++ph)
+    for (int pw = 0; pw < st; ++pw) {
+      const int I = (d->H - ph + st - 1) / st;
+      const int J = (d->W - pw + st - 1) / st;
+      if (I <= 0 || J <= 0) continue;
+      IgemmLaunch L;
+      memset(&L, 0, sizeof(L));
+      int dh[kMaxTaps], dwv[kMaxTaps], rr[kMaxTaps], ss[kMaxTaps];
+      int nr = 0, ns = 0;
+      for (int r = 0; r < d->R; ++r) {
+        const int v = ph + d->pad_h - r;
+        if (((v % st) + st) % st == 0) { dh[nr] = (v - (((v % st) + st) % st)) / st; rr[nr] = r; ++nr; }
+      }
+      for (int s = 0; s < d->S; ++s) {
+        const int v = pw + d->pad_w - s;
+        if (((v % st) + st) % st == 0) { dwv[ns] = (v - (((v % st) + st) % st)) / st; ss[ns] = s; ++ns; }
+      }
+      if (nr * ns == 0) continue;
+      int lo_h = dh[0], lo_w = dwv[0];
+      for (int i = 1; i < nr; ++i) lo_h = dh[i] < lo_h ? dh[i] : lo_h;
+      for (int i = 1; i < ns; ++i) lo_w = dwv[i] < lo_w ? dwv[i] : lo_w;
+      L.ntaps = nr * ns;
+      for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < ns; ++b) {
+          TapEntry& t = L.taps[a * ns + b];
+          t.off_h = (uint16_t)(dh[a] - lo_h);
+          t.off_w = (uint16_t)(dwv[b] - lo_w);
+          t.b_tap = (uint16_t)(rr[a] * d->S + ss[b]);
+          t.pad_ = 0;
+        }
+      L.src = dy; L.Nimg = d->N; L.SH = d->P; L.SW = d->Q; L.SC = d->K;
+      L.wmat = wt; L.Nout = d->C; L.wtaps = d->R * d->S;
+      L.I = I; L.J = J; L.trav = 1; L.lower_w = lo_w; L.lower_h = lo_h;
+      L.out = dx; L.OH = d->H; L.OW = d->W; L.os = st; L.oh0 = ph; L.ow0 = pw; L.ldo = d->C;
+      L.res = residual; L.bias = nullptr; L.act = 0; L.out_fp32 = 0;
+      rc = launch_igemm(L, stream);
+      if (rc) return rc;
+    }
+  return B200_OK;
+}
+
+extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, float* dw,
+                               b200_stream_t stream_) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_REQUIRE(x && dy && dw, B200_ERR_INVALID, "conv_wgrad: null pointer");
+  B200_REQUIRE(d->C % 8 == 0 && d->K % 8 == 0, B200_ERR_UNSUPPORTED,
+               "conv_wgrad: C=%d and K=%d must be multiples of 8", d->C, d->K);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.M_total = d->N * d->P * d->Q;
+  p.P = d->P; p.Q = d->Q; p.trav = d->stride; p.lower_w = -d->pad_w; p.lower_h = -d->pad_h;
+  p.K_out = d->K; p.C = d->C; p.taps_total = d->R * d->S;
+  p.ckA = pick_ck(d->K);
+  p.ckB = pick_ck(d->C);
+  p.bk = 32;
+  p.c_chunks = (d->C + p.ckB - 1) / p.ckB;
+  p.total_boxes = p.taps_total * p.c_chunks;
+  p.boxes_per_cta = 512 / p.ckB;
+  if (p.boxes_per_cta > 8) p.boxes_per_cta = 8;
+  if (p.boxes_per_cta > p.total_boxes) p.boxes_per_cta = p.total_boxes;
+  p.k_tiles = (d->K + kTileM - 1) / kTileM;
+  p.col_groups = (p.total_boxes + p.boxes_per_cta - 1) / p.boxes_per_cta;
+  p.total_blocks = (p.M_total + p.bk - 1) / p.bk;
+  const int tiles = p.k_tiles * p.col_groups;
+  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  if (splits > p.total_blocks) splits = p.total_blocks;
+  if (splits < 1) splits = 1;
+  p.blocks_per_split = (p.total_blocks + splits - 1) / splits;
+  p.splits = (p.total_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
+  p.boxA_bytes = p.bk * p.ckA * 2;
+  p.boxB_bytes = p.bk * p.ckB * 2;
+  p.stage_bytes = (kTileM / p.ckA) * p.boxA_bytes + p.boxes_per_cta * p.boxB_bytes;
+  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
+  p.num_stages = kSmemBudget / (int)p.stage_bytes;
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  if (p.num_stages < 2) p.num_stages = 2;
+  p.dw = dw;
+  for (int r = 0; r < d->R; ++r)
+    for (int s = 0; s < d->S; ++s) {
+      TapEntry& t = p.taps[r * d->S + s];
+      t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.b_tap = (uint16_t)(r * d->S + s); t.pad_ = 0;
+    }
+  CUtensorMap tmDy, tmX;
+  rc = encode_tiled2(&tmDy, dy, d->K, (long long)p.M_total, p.ckA, p.bk);
+  if (rc) return rc;
+  const int upper_w = p.lower_w + (d->Q - 1) * d->stride + 1 - d->W;
+  const int upper_h = p.lower_h + (d->P - 1) * d->stride + 1 - d->H;
+  rc = encode_im2col(&tmX, x, d->N, d->H, d->W, d->C, p.ckB, p.bk, p.lower_w, p.lower_h, upper_w, upper_h,
+                     d->stride);
+  if (rc) return rc;
+  const int smem_bytes = p.num_stages * (int)p.stage_bytes + 1024;
+  rc = set_smem_attr((const void*)conv_wgrad_kernel, smem_bytes);
+  if (rc) return rc;
+  const int grid = tiles * p.splits;
+  conv_wgrad_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmDy, tmX, p);
+  B200_CHECK_LAUNCH("conv_wgrad_kernel");
+  return B200_OK;
+}

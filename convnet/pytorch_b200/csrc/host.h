@@ -1,0 +1,49 @@
+// Host-side plumbing shared by the C-ABI translation units: error text, launch counting,
+// driver entry points for tensor-map encoding (resolved at run time: no libcuda link dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include "../../../include/b200conv.h"
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int sm_count();
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();
+EncodeIm2colFn encode_im2col_fn();
+
+inline CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+#define B200_CHECK_LAUNCH(name)                                                   \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      b200::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+      return B200_ERR_CUDA;                                                       \
+    }                                                                             \
+    b200::count_launch();                                                         \
+  } while (0)
+
+#define B200_REQUIRE(cond, code, ...)   \
+  do {                                  \
+    if (!(cond)) {                      \
+      b200::set_error(__VA_ARGS__);     \
+      return code;                      \
+    }                                   \
+  } while (0)
+
+}  // namespace b200

@@ -1,0 +1,203 @@
+// Pooling for NHWC bf16: 3x3/s2/p1 max pool (argmax kept as one byte per output element so backward
+// is a deterministic gather) and global average pool.  HBM-bound, 128-bit vectorised.
+// Replaces nn.MaxPool2d(3,2,1) (models/resnet.py:230) and nn.AdaptiveAvgPool2d(1)
+// (models/resnet.py:241,341; models/mobilenet_v2.py:124) forward and backward.
+#include "common.cuh"
+#include "host.h"
+#include <math_constants.h>
+
+namespace b200 {
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W,
+                                                          int C, int OH, int OW, __nv_bfloat16* __restrict__ y,
+                                                          uint8_t* __restrict__ amax) {
+  const int cv = C >> 3;
+  const long long total = (long long)N * OH * OW * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % cv);
+    long long pix = idx / cv;
+    const int q = (int)(pix % OW); pix /= OW;
+    const int p = (int)(pix % OH);
+    const int n = (int)(pix / OH);
+    float best[8];
+    int bidx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best[i] = -CUDART_INF_F; bidx[i] = 0; }
+    bool first = true;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * p - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * q - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        ld8(x + (((long long)n * H + h) * W + w) * C + v * 8, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // first occurrence wins on ties (strict >), NaN propagates, like ATen's max_pool2d
+          if (first || f[i] > best[i] || f[i] != f[i]) { best[i] = f[i]; bidx[i] = r * 3 + s; }
+        }
+        first = false;
+      }
+    }
+    const long long o = (((long long)n * OH + p) * OW + q) * C + v * 8;
+    st8(y + o, best);
+    if (amax != nullptr) {
+      uint2 pk;
+      pk.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+      pk.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+      *reinterpret_cast<uint2*>(amax + o) = pk;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const uint8_t* __restrict__ amax, int N, int H, int W, int C,
+                                                          int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  const int cv = C >> 3;
+  const long long total = (long long)N * H * W * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % cv);
+    long long pix = idx / cv;
+    const int w = (int)(pix % W); pix /= W;
+    const int h = (int)(pix % H);
+    const int n = (int)(pix / H);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // windows containing h: 2p-1 <= h <= 2p+1
+    const int p_lo = h / 2, p_hi = (h + 1) / 2;
+    const int q_lo = w / 2, q_hi = (w + 1) / 2;
+    for (int p = p_lo; p <= p_hi; ++p) {
+      if (p >= OH) continue;
+      const int r = h - (2 * p - 1);
+      for (int q = q_lo; q <= q_hi; ++q) {
+        if (q >= OW) continue;
+        const int s = w - (2 * q - 1);
+        const int want = r * 3 + s;
+        const long long o = (((long long)n * OH + p) * OW + q) * C + v * 8;
+        const uint2 pk = *reinterpret_cast<const uint2*>(amax + o);
+        float g[8];
+        ld8(dy + o, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int b = (i < 4 ? (pk.x >> (8 * i)) : (pk.y >> (8 * (i - 4)))) & 0xff;
+          if (b == want) acc[i] += g[i];
+        }
+      }
+    }
+    st8(dx + (((long long)n * H + h) * W + w) * C + v * 8, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int HW, int C,
+                                                          __nv_bfloat16* __restrict__ y) {
+  const int cv = C >> 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * cv) return;
+  const int n = idx / cv, v = idx - n * cv;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const __nv_bfloat16* base = x + (long long)n * HW * C + v * 8;
+  for (int i = 0; i < HW; ++i) {
+    float f[8];
+    ld8(base + (long long)i * C, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+  const float inv = 1.f / (float)HW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] *= inv;
+  st8(y + (long long)n * C + v * 8, acc);
+}
+
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int N, int HW, int C,
+                                                          __nv_bfloat16* __restrict__ dx) {
+  const int cv = C >> 3;
+  const long long total = (long long)N * HW * cv;
+  const float inv = 1.f / (float)HW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % cv);
+    const long long pix = idx / cv;
+    const int n = (int)(pix / HW);
+    float g[8];
+    ld8(dy + (long long)n * C + v * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= inv;
+    st8(dx + pix * C + v * 8, g);
+  }
+}
+
+static inline int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* y, uint8_t* argmax,
+                                     b200_stream_t stream) {
+  B200_REQUIRE(x && y && N > 0 && H > 0 && W > 0, B200_ERR_INVALID, "maxpool_fwd: bad argument");
+  B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "maxpool_fwd: C=%d must be a multiple of 8", C);
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * OH * OW * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, OH,
+                                                                           OW, (__nv_bfloat16*)y, argmax);
+  B200_CHECK_LAUNCH("maxpool_fwd_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, int N, int H, int W, int C, void* dx,
+                                     b200_stream_t stream) {
+  B200_REQUIRE(dy && argmax && dx && N > 0, B200_ERR_INVALID, "maxpool_bwd: bad argument");
+  B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "maxpool_bwd: C=%d must be a multiple of 8", C);
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, argmax, N, H, W,
+                                                                           C, OH, OW, (__nv_bfloat16*)dx);
+  B200_CHECK_LAUNCH("maxpool_bwd_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_avgpool_fwd(const void* x, int N, int HW, int C, void* y, b200_stream_t stream) {
+  B200_REQUIRE(x && y && N > 0 && HW > 0, B200_ERR_INVALID, "avgpool_fwd: bad argument");
+  B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "avgpool_fwd: C=%d must be a multiple of 8", C);
+  const int total = N * (C / 8);
+  avgpool_fwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, HW, C,
+                                                                          (__nv_bfloat16*)y);
+  B200_CHECK_LAUNCH("avgpool_fwd_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_avgpool_bwd(const void* dy, int N, int HW, int C, void* dx, b200_stream_t stream) {
+  B200_REQUIRE(dy && dx && N > 0 && HW > 0, B200_ERR_INVALID, "avgpool_bwd: bad argument");
+  B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "avgpool_bwd: C=%d must be a multiple of 8", C);
+  const long long total = (long long)N * HW * (C / 8);
+  avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, N, HW, C,
+                                                                           (__nv_bfloat16*)dx);
+  B200_CHECK_LAUNCH("avgpool_bwd_kernel");
+  return B200_OK;
+}

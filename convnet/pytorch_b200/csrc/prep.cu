@@ -1,0 +1,176 @@
+// Layout / precision transforms around the tensor-core kernels:
+//  - network input NCHW fp32 -> NHWC bf16 (channel padded) or space-to-depth NHWC bf16 for the 7x7/s2 stem
+//    (replaces inputs.to(device, dtype), trainer.py:116-117, plus the relayout cuDNN does internally)
+//  - weight relayouts: [K][T][C] -> [C][T][K] for dgrad, 7x7 stem <-> 4x4 space-to-depth form
+//  - fp32 -> bf16 cast of flat arrays
+#include "common.cuh"
+#include "host.h"
+
+namespace b200 {
+
+__global__ void __launch_bounds__(256) input_prep_kernel(const float* __restrict__ x, int N, int C, int H, int W,
+                                                         int Cpad, int mode, __nv_bfloat16* __restrict__ out) {
+  // one thread per output pixel; Cpad is a multiple of 8
+  const int OH = mode == 1 ? H / 2 : H, OW = mode == 1 ? W / 2 : W;
+  const long long total = (long long)N * OH * OW;
+  const long long plane = (long long)H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % OW);
+    const int i = (int)((idx / OW) % OH);
+    const int n = (int)(idx / ((long long)OW * OH));
+    __nv_bfloat16* o = out + idx * Cpad;
+    const float* xi = x + (long long)n * C * plane;
+    for (int c0 = 0; c0 < Cpad; c0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = c0 + e;
+        float val = 0.f;
+        if (mode == 0) {
+          if (ch < C) val = __ldg(xi + (long long)ch * plane + (long long)i * W + j);
+        } else {
+          const int sub = ch / C, c = ch - sub * C;  // sub = dy*2+dx
+          if (sub < 4) {
+            const int dy = sub >> 1, dx = sub & 1;
+            val = __ldg(xi + (long long)c * plane + (long long)(2 * i + dy) * W + (2 * j + dx));
+          }
+        }
+        f[e] = val;
+      }
+      uint4 u;
+      u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+      u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(o + c0) = u;
+    }
+  }
+}
+
+// bf16 [K][T][C] -> [C][T][K]; one 32x32 tile per block, blockIdx.z = tap
+__global__ void __launch_bounds__(256) weight_transpose_kernel(const __nv_bfloat16* __restrict__ src,
+                                                               __nv_bfloat16* __restrict__ dst, int K, int T, int C) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int t = blockIdx.z;
+  const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, c = c0 + tx;
+    tile[r][tx] = (k < K && c < C) ? src[((long long)k * T + t) * C + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, k = k0 + tx;
+    if (c < C && k < K) dst[((long long)c * T + t) * K + k] = tile[tx][r];
+  }
+}
+
+// stem: w fp32 [K][7][7][C] -> bf16 [K][16][Cpad], tap (ah,aw) in 4x4, channel (bh*2+bw)*C + c,
+// r = 2*ah + bh - 1, s = 2*aw + bw - 1 (out-of-range -> 0)
+__global__ void stem_w_to_s2d_kernel(const float* __restrict__ w, int K, int C, int Cpad,
+                                     __nv_bfloat16* __restrict__ out) {
+  const int total = K * 16 * Cpad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ch = idx % Cpad;
+    const int tap = (idx / Cpad) % 16;
+    const int k = idx / (Cpad * 16);
+    const int ah = tap >> 2, aw = tap & 3;
+    float val = 0.f;
+    const int sub = ch / C, c = ch - sub * C;
+    if (sub < 4) {
+      const int r = 2 * ah + (sub >> 1) - 1, s = 2 * aw + (sub & 1) - 1;
+      if (r >= 0 && r < 7 && s >= 0 && s < 7) val = w[(((long long)k * 7 + r) * 7 + s) * C + c];
+    }
+    out[idx] = __float2bfloat16(val);
+  }
+}
+// reverse gather for the gradient: dw[K][7][7][C] += dw_s2d[K][16][Cpad]
+__global__ void stem_wgrad_from_s2d_kernel(const float* __restrict__ dws, int K, int C, int Cpad,
+                                           float* __restrict__ dw) {
+  const int total = K * 49 * C;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx % C;
+    const int s = (idx / C) % 7;
+    const int r = (idx / (C * 7)) % 7;
+    const int k = idx / (C * 49);
+    const int ah = (r + 1) >> 1, bh = (r + 1) & 1, aw = (s + 1) >> 1, bw = (s + 1) & 1;
+    dw[idx] += dws[((long long)k * 16 + ah * 4 + aw) * Cpad + (bh * 2 + bw) * C + c];
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src,
+                                                            __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + i);
+    uint2 u;
+    u.x = pack_bf16x2(f.x, f.y);
+    u.y = pack_bf16x2(f.z, f.w);
+    reinterpret_cast<uint2*>(dst)[i] = u;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+static inline int grid_cap(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_input_prep(const float* x, int N, int C, int H, int W, int Cpad, int mode, void* out,
+                               b200_stream_t stream) {
+  B200_REQUIRE(x && out && N > 0 && C > 0 && H > 0 && W > 0, B200_ERR_INVALID, "input_prep: bad argument");
+  B200_REQUIRE(Cpad % 8 == 0, B200_ERR_UNSUPPORTED, "input_prep: Cpad=%d must be a multiple of 8", Cpad);
+  if (mode == 0) {
+    B200_REQUIRE(Cpad >= C, B200_ERR_INVALID, "input_prep: Cpad < C");
+  } else if (mode == 1) {
+    B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cpad >= 4 * C, B200_ERR_UNSUPPORTED,
+                 "input_prep: space-to-depth needs even H,W and Cpad >= 4C");
+  } else {
+    B200_REQUIRE(false, B200_ERR_INVALID, "input_prep: unknown mode %d", mode);
+  }
+  const long long total = (long long)N * (mode == 1 ? (H / 2) * (W / 2) : H * W);
+  input_prep_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(x, N, C, H, W, Cpad, mode,
+                                                                          (__nv_bfloat16*)out);
+  B200_CHECK_LAUNCH("input_prep_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_weight_transpose(const void* src, void* dst, int K, int T, int C, b200_stream_t stream) {
+  B200_REQUIRE(src && dst && K > 0 && T > 0 && C > 0, B200_ERR_INVALID, "weight_transpose: bad argument");
+  dim3 grid((C + 31) / 32, (K + 31) / 32, T);
+  weight_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, K, T,
+                                                                C);
+  B200_CHECK_LAUNCH("weight_transpose_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_stem_weight_to_s2d(const float* w, int K, int C, int Cpad, void* w_s2d, b200_stream_t stream) {
+  B200_REQUIRE(w && w_s2d && K > 0 && C > 0 && Cpad >= 4 * C, B200_ERR_INVALID, "stem_weight_to_s2d: bad argument");
+  stem_w_to_s2d_kernel<<<(K * 16 * Cpad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, K, C, Cpad,
+                                                                                    (__nv_bfloat16*)w_s2d);
+  B200_CHECK_LAUNCH("stem_w_to_s2d_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_stem_wgrad_from_s2d(const float* dw_s2d, int K, int C, int Cpad, float* dw, b200_stream_t stream) {
+  B200_REQUIRE(dw_s2d && dw && K > 0 && C > 0 && Cpad >= 4 * C, B200_ERR_INVALID, "stem_wgrad_from_s2d: bad argument");
+  stem_wgrad_from_s2d_kernel<<<(K * 49 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dw_s2d, K, C, Cpad, dw);
+  B200_CHECK_LAUNCH("stem_wgrad_from_s2d_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, b200_stream_t stream) {
+  B200_REQUIRE(src && dst && n >= 0, B200_ERR_INVALID, "cast_f32_to_bf16: bad argument");
+  if (n == 0) return B200_OK;
+  cast_f32_bf16_kernel<<<grid_cap((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  B200_CHECK_LAUNCH("cast_f32_bf16_kernel");
+  return B200_OK;
+}

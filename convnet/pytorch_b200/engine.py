@@ -1,0 +1,463 @@
+"""B200 execution engine: parameter arenas + the fused forward/backward pipeline of the ResNet family.
+
+``convert_b200(model)`` takes a model built by the registry (ordinary ``torch.nn`` layers, reference
+attribute names) and
+  * moves every parameter into flat device arenas -- fp32 master ``p32``, fp32 gradient ``g32``, bf16
+    compute shadow ``p16`` -- conv weights physically [K][R*S][C] (the layout the tcgen05 kernels read)
+    while ``param.shape`` / ``state_dict()`` stay the reference's logical OIHW (SURVEY.md section 5,
+    checkpoint row);
+  * installs a runtime whose ``forward`` replaces ``model.forward`` (models/resnet.py:196-213 in the
+    reference) by the kernel pipeline
+        conv (tcgen05 implicit GEMM) -> BN statistics -> BN apply + ReLU (+ residual) ...
+    and whose backward (one autograd node for the whole net) runs BN backward, dgrad and wgrad kernels
+    and writes parameter gradients straight into ``g32`` (``param.grad`` are views of it).
+Nothing here computes on the CPU or through cuDNN/cuBLAS: a missing library or an unsupported layer
+raises ``B200Error``.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .lib import B200Error, ACT_NONE, ACT_RELU, ACT_RELU6
+
+_ALIGN = 64  # elements; keeps every slot 128B-aligned in the bf16 shadow (TMA needs 16B)
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class _Slot(object):
+    __slots__ = ('name', 'param', 'kind', 'offset', 'numel', 'alloc', 'shape', 'group', 'module')
+
+
+class Arena(object):
+    """Flat fp32 master / fp32 grad / bf16 shadow storage for all parameters of one model."""
+
+    def __init__(self, model, device):
+        self.device = device
+        slots = []
+        seen = set()
+        for mod_name, mod in model.named_modules():
+            for p_name, p in mod.named_parameters(recurse=False):
+                if id(p) in seen:
+                    continue
+                seen.add(id(p))
+                s = _Slot()
+                s.name = (mod_name + '.' if mod_name else '') + p_name
+                s.param, s.module, s.shape = p, mod, tuple(p.shape)
+                s.numel = p.numel()
+                s.alloc = s.numel
+                if isinstance(mod, nn.Conv2d) and p_name == 'weight':
+                    depthwise = mod.groups > 1 and mod.groups == mod.in_channels and mod.in_channels == mod.out_channels
+                    if mod.groups > 1 and not depthwise:
+                        raise B200Error('grouped convolution (groups=%d) in %s is not served by the B200 kernels yet'
+                                        % (mod.groups, s.name))
+                    s.kind = 'dw' if depthwise else 'conv'
+                    s.group = 1 if depthwise else 0
+                elif isinstance(mod, nn.Linear) and p_name == 'weight':
+                    s.kind, s.group = 'fc', 0
+                    s.alloc = _round_up(p.shape[0], 8) * p.shape[1]  # zero rows: class count padded to 8
+                elif isinstance(mod, nn.Linear) and p_name == 'bias':
+                    s.kind, s.group = 'vec', 2
+                    s.alloc = _round_up(p.shape[0], 8)
+                else:
+                    s.kind, s.group = 'vec', 2
+                slots.append(s)
+        slots.sort(key=lambda s: s.group)  # stable: [dense conv + fc | depthwise | everything else]
+        off = 0
+        self.group_end = [0, 0, 0]
+        for s in slots:
+            s.offset = off
+            off += _round_up(s.alloc, _ALIGN)
+            self.group_end[s.group] = off
+        self.group_end[1] = max(self.group_end[1], self.group_end[0])
+        self.group_end[2] = off
+        self.total = off
+        self.slots = slots
+        self.by_param = {id(s.param): s for s in slots}
+        self.p32 = torch.zeros(off, device=device, dtype=torch.float32)
+        self.g32 = torch.zeros(off, device=device, dtype=torch.float32)
+        self.p16 = torch.zeros(off, device=device, dtype=torch.bfloat16)
+        with torch.no_grad():
+            for s in slots:
+                src = s.param.detach().to(device=device, dtype=torch.float32)
+                view = self.logical_view(self.p32, s)
+                view.copy_(src)
+                s.param.data = view
+                s.param.grad = self.logical_view(self.g32, s)
+        self.sync_shadow()
+
+    # logical (reference-shaped) view of a slot inside a flat buffer
+    def logical_view(self, flat, s):
+        seg = flat[s.offset:s.offset + s.numel]
+        if s.kind == 'conv':
+            K, C, R, S = s.shape
+            return seg.view(K, R, S, C).permute(0, 3, 1, 2)
+        if s.kind == 'dw':
+            C, _, R, S = s.shape
+            return seg.view(R, S, C).permute(2, 0, 1).unsqueeze(1)
+        return seg.view(s.shape)
+
+    def kernel_view(self, flat, s):
+        """physical layout consumed by the kernels."""
+        if s.kind == 'conv':
+            K, C, R, S = s.shape
+            return flat[s.offset:s.offset + s.numel].view(K, R * S, C)
+        if s.kind == 'dw':
+            C, _, R, S = s.shape
+            return flat[s.offset:s.offset + s.numel].view(R * S, C)
+        if s.kind == 'fc':
+            K, C = s.shape
+            return flat[s.offset:s.offset + s.alloc].view(_round_up(K, 8), 1, C)
+        return flat[s.offset:s.offset + s.alloc]
+
+    def slot(self, param):
+        return self.by_param[id(param)]
+
+    def sync_shadow(self):
+        """bf16 shadow <- fp32 master (whole arena, one kernel)."""
+        ops.cast_bf16(self.p32, self.p16)
+
+    def zero_grad(self):
+        self.g32.zero_()
+
+    def rebind_grads(self):
+        for s in self.slots:
+            if s.param.grad is None or s.param.grad.data_ptr() != self.g32.data_ptr() + 4 * s.offset:
+                s.param.grad = self.logical_view(self.g32, s)
+
+
+# ----------------------------------------------------------------------------------------------------
+class _Conv(object):
+    def __init__(self, arena, mod):
+        s = arena.slot(mod.weight)
+        self.kind = s.kind
+        self.K, self.C = mod.out_channels, mod.in_channels
+        self.R, self.S = mod.kernel_size
+        self.stride = mod.stride[0]
+        self.pad = mod.padding[0]
+        if mod.stride[0] != mod.stride[1] or mod.padding[0] != mod.padding[1] or mod.dilation != (1, 1) \
+                or mod.bias is not None:
+            raise B200Error('conv %s: only square stride/padding, dilation 1 and bias=False are supported' % s.name)
+        self.w16 = arena.kernel_view(arena.p16, s)
+        self.w32 = arena.kernel_view(arena.p32, s)
+        self.g32 = arena.kernel_view(arena.g32, s)
+
+    def desc(self, N, H, W):
+        return ops.make_desc(N, H, W, self.C, self.K, self.R, self.S, self.stride, self.pad)
+
+
+class _BN(object):
+    def __init__(self, arena, mod):
+        if not mod.affine or not mod.track_running_stats:
+            raise B200Error('BatchNorm2d without affine/running stats is not supported')
+        self.mod = mod
+        self.C = mod.num_features
+        sw, sb = arena.slot(mod.weight), arena.slot(mod.bias)
+        self.gamma = arena.kernel_view(arena.p32, sw)
+        self.beta = arena.kernel_view(arena.p32, sb)
+        self.dgamma = arena.kernel_view(arena.g32, sw)
+        self.dbeta = arena.kernel_view(arena.g32, sb)
+
+
+class _Unit(object):
+    """saved state of one conv+BN unit for backward."""
+    __slots__ = ('x', 'z', 'y', 'desc', 'mean', 'invstd', 'scale', 'shift', 'sums', 'conv', 'bn', 'act')
+
+
+class Runtime(object):
+    """Kernel pipeline for one converted model.  ``forward(x)`` takes the reference's NCHW fp32 input."""
+
+    def __init__(self, model, device):
+        self.model = model
+        self.device = device
+        self.arena = Arena(model, device)
+        for name, buf in model.named_buffers():
+            buf.data = buf.data.to(device)
+        self._anchor = self.arena.slots[0].param
+        self._max_c = max([m.num_features for m in model.modules() if isinstance(m, nn.BatchNorm2d)] + [8])
+        self._ws = torch.empty(ops.bn_workspace_floats(self._max_c), device=device, dtype=torch.float32)
+        self.loss_scale_inv = 1.0
+        self._build()
+
+    # ---- program construction (overridden per model family) -------------------------------------
+    def _build(self):
+        raise NotImplementedError
+
+    # ---- small helpers ----------------------------------------------------------------------------
+    def _coeffs(self, n):
+        return torch.empty(n, device=self.device, dtype=torch.float32)
+
+    def _unit_fwd(self, x, conv, bn, act, training, tape, residual=None, other=None):
+        """z = conv(x); BN statistics (train) / running-stat coefficients (eval);
+        y = act(bn(z) + residual | + bn_other(z_other)).  Returns y and (if tape) the saved unit."""
+        N, H, W, _ = x.shape
+        u = _Unit()
+        u.conv, u.bn, u.act, u.x = conv, bn, act, x
+        u.desc = conv.desc(N, H, W)
+        u.z = ops.conv_fprop(x, conv.w16, u.desc)
+        self._bn_coeffs(u, training)
+        if other is not None:
+            u.y = ops.bn_apply(u.z, u.scale, u.shift, act, z2=other.z, scale2=other.scale, shift2=other.shift)
+        else:
+            u.y = ops.bn_apply(u.z, u.scale, u.shift, act, residual=residual)
+        return u
+
+    def _bn_coeffs(self, u, training):
+        bn = u.bn
+        C = bn.C
+        buf = self._coeffs(6 * C)
+        u.mean, u.invstd, u.scale, u.shift, u.sums = buf[0:C], buf[C:2 * C], buf[2 * C:3 * C], buf[3 * C:4 * C], \
+            buf[4 * C:6 * C]
+        m = bn.mod
+        if training:
+            ops.bn_stats(u.z, bn.gamma, bn.beta, m.eps, m.momentum, m.running_mean, m.running_var,
+                         m.num_batches_tracked, u.mean, u.invstd, u.scale, u.shift, self._ws)
+        else:
+            ops.bn_eval_coeffs(bn.gamma, bn.beta, m.running_mean, m.running_var, m.eps, u.scale, u.shift)
+
+    def _stats_only(self, x, conv, bn, training):
+        """conv + BN coefficients without the apply (used for the downsample branch, fused into the main apply)."""
+        N, H, W, _ = x.shape
+        u = _Unit()
+        u.conv, u.bn, u.act, u.x = conv, bn, ACT_NONE, x
+        u.desc = conv.desc(N, H, W)
+        u.z = ops.conv_fprop(x, conv.w16, u.desc)
+        self._bn_coeffs(u, training)
+        u.y = None
+        return u
+
+    def _bn_bwd(self, u, dy, y_mask, act, want_g=False):
+        """BN (+activation) backward of unit u: returns dz (and g = dy*act'(y) when want_g)."""
+        ops.bn_bwd_reduce(dy, y_mask if act != ACT_NONE else None, u.z, act, u.mean, u.invstd, u.sums,
+                          u.bn.dgamma, u.bn.dbeta, self._ws)
+        g = torch.empty_like(dy) if want_g else None
+        dz = ops.bn_bwd_dx(dy, y_mask if act != ACT_NONE else None, u.z, act, u.mean, u.invstd, u.bn.gamma, u.sums,
+                           g_out=g)
+        return dz, g
+
+    def _conv_bwd(self, u, dz, need_dx=True, residual=None):
+        """wgrad into the gradient arena and (optionally) dgrad."""
+        ops.conv_wgrad(u.x, dz, u.desc, u.conv.g32)
+        if not need_dx:
+            return None
+        wt = ops.weight_transpose(u.conv.w16)
+        return ops.conv_dgrad(dz, wt, u.desc, residual=residual)
+
+    # ---- autograd glue ----------------------------------------------------------------------------
+    def forward(self, x):
+        if x.device.type != 'cuda':
+            raise B200Error('B200 runtime needs CUDA inputs (no CPU fallback); got %s' % x.device)
+        training = self.model.training
+        if torch.is_grad_enabled():
+            return _NetFn.apply(x, self._anchor, self, training)
+        logits, _ = self.run_forward(x, training, False)
+        return logits
+
+    def run_forward(self, x, training, want_tape):
+        raise NotImplementedError
+
+    def run_backward(self, tape, dlogits):
+        raise NotImplementedError
+
+
+class _NetFn(torch.autograd.Function):
+    """One autograd node for the whole network: backward writes parameter gradients into the arena."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, rt, training):
+        logits, tape = rt.run_forward(x.detach(), training, True)
+        ctx.rt, ctx.tape = rt, tape
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        rt, tape = ctx.rt, ctx.tape
+        ctx.tape = None
+        rt.arena.rebind_grads()
+        rt.run_backward(tape, dlogits)
+        return None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------
+class ResNetRuntime(Runtime):
+    """Pipeline for models.resnet.ResNet_imagenet / ResNet_cifar (BasicBlock or Bottleneck)."""
+
+    def _build(self):
+        from .models.resnet import BasicBlock, Bottleneck
+        m, a = self.model, self.arena
+        self.imagenet_stem = m.conv1.kernel_size == (7, 7)
+        if self.imagenet_stem:
+            if m.conv1.stride != (2, 2) or m.conv1.padding != (3, 3) or m.conv1.in_channels != 3:
+                raise B200Error('unsupported 7x7 stem geometry')
+        elif m.conv1.kernel_size != (3, 3) or m.conv1.stride != (1, 1) or m.conv1.in_channels > 16:
+            raise B200Error('unsupported stem geometry')
+        self.stem_conv = m.conv1
+        s = a.slot(m.conv1.weight)
+        self.stem_w32 = a.p32[s.offset:s.offset + s.numel]      # [K][R][S][C] fp32
+        self.stem_g32 = a.g32[s.offset:s.offset + s.numel]
+        self.stem_bn = _BN(a, m.bn1)
+        self.has_maxpool = isinstance(m.maxpool, nn.MaxPool2d)
+        self.blocks = []
+        for lname in ('layer1', 'layer2', 'layer3', 'layer4'):
+            layer = getattr(m, lname)
+            if isinstance(layer, nn.Identity):
+                continue
+            for blk in layer:
+                if blk.residual_block is not None:
+                    raise B200Error('residual_block (SE) is outside the B200 hot path')
+                if isinstance(blk.dropout, nn.Dropout) and blk.dropout.p != 0:
+                    raise B200Error('dropout inside residual blocks is not supported on the B200 path')
+                spec = {'kind': 'bottleneck' if isinstance(blk, Bottleneck) else 'basic'}
+                if not isinstance(blk, (BasicBlock, Bottleneck)):
+                    raise B200Error('unknown block type %s' % type(blk).__name__)
+                names = ('conv1', 'conv2', 'conv3') if spec['kind'] == 'bottleneck' else ('conv1', 'conv2')
+                spec['convs'] = [_Conv(a, getattr(blk, n)) for n in names]
+                spec['bns'] = [_BN(a, getattr(blk, n.replace('conv', 'bn'))) for n in names]
+                spec['down'] = None
+                if blk.downsample is not None:
+                    spec['down'] = (_Conv(a, blk.downsample[0]), _BN(a, blk.downsample[1]))
+                self.blocks.append(spec)
+        fc = m.fc
+        sw, sb = a.slot(fc.weight), a.slot(fc.bias)
+        self.classes = fc.out_features
+        self.classes_pad = _round_up(self.classes, 8)
+        self.fc_in = fc.in_features
+        self.fc_w16 = a.kernel_view(a.p16, sw)       # [Kpad,1,C]
+        self.fc_gw = a.kernel_view(a.g32, sw)
+        self.fc_b = a.kernel_view(a.p32, sb)         # [Kpad]
+        self.fc_gb = a.kernel_view(a.g32, sb)
+
+    # ---- stem ---------------------------------------------------------------------------------------
+    def _stem_fwd(self, x, training):
+        N, Cin, H, W = x.shape
+        K = self.stem_conv.out_channels
+        x = x.float().contiguous()
+        st = {}
+        if self.imagenet_stem:
+            xs = ops.input_prep(x, 16, s2d=True)                       # [N, H/2, W/2, 16]
+            ws = torch.empty((K, 16, 16), device=self.device, dtype=torch.bfloat16)
+            ops.stem_weight_to_s2d(self.stem_w32, K, Cin, 16, ws)
+            desc = ops.make_desc(N, H // 2, W // 2, 16, K, 4, 4, 1, 2, P=H // 2, Q=W // 2)
+        else:
+            xs = ops.input_prep(x, 16, s2d=False)
+            ws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.bfloat16)
+            ws[:, :, :Cin].copy_(self.stem_w32.view(K, 9, Cin))       # 432-element pad+cast of the 3-channel stem
+            desc = ops.make_desc(N, H, W, 16, K, 3, 3, 1, 1)
+        u = _Unit()
+        u.conv, u.bn, u.act, u.x, u.desc = None, self.stem_bn, ACT_RELU, xs, desc
+        u.z = ops.conv_fprop(xs, ws, desc)
+        self._bn_coeffs(u, training)
+        u.y = ops.bn_apply(u.z, u.scale, u.shift, ACT_RELU)
+        st['unit'] = u
+        out = u.y
+        if self.has_maxpool:
+            out, st['argmax'] = ops.maxpool_fwd(u.y)
+        st['cin'] = Cin
+        return out, st
+
+    def _stem_bwd(self, st, dy):
+        u = st['unit']
+        if self.has_maxpool:
+            dy = ops.maxpool_bwd(dy, st['argmax'], tuple(u.y.shape))
+        dz, _ = self._bn_bwd(u, dy, u.y, ACT_RELU)
+        K, Cin = self.stem_conv.out_channels, st['cin']
+        if self.imagenet_stem:
+            dws = torch.zeros((K, 16, 16), device=self.device, dtype=torch.float32)
+            ops.conv_wgrad(u.x, dz, u.desc, dws)
+            ops.stem_wgrad_from_s2d(dws, K, Cin, 16, self.stem_g32)
+        else:
+            dws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.float32)
+            ops.conv_wgrad(u.x, dz, u.desc, dws)
+            self.stem_g32.view(K, 9, Cin).add_(dws[:, :, :Cin])
+
+    # ---- residual blocks ----------------------------------------------------------------------------
+    def _block_fwd(self, spec, x, training):
+        convs, bns = spec['convs'], spec['bns']
+        units = []
+        h = x
+        for i in range(len(convs) - 1):
+            u = self._unit_fwd(h, convs[i], bns[i], ACT_RELU, training, True)
+            units.append(u)
+            h = u.y
+        down = None
+        if spec['down'] is not None:
+            down = self._stats_only(x, spec['down'][0], spec['down'][1], training)
+            last = self._unit_fwd(h, convs[-1], bns[-1], ACT_RELU, training, True, other=down)
+        else:
+            last = self._unit_fwd(h, convs[-1], bns[-1], ACT_RELU, training, True, residual=x)
+        units.append(last)
+        return last.y, {'units': units, 'down': down}
+
+    def _block_bwd(self, spec, saved, dy):
+        units, down = saved['units'], saved['down']
+        last = units[-1]
+        # out = relu(bn_last(z) + skip): g = dy * (out > 0) feeds both branches
+        dz, g = self._bn_bwd(last, dy, last.y, ACT_RELU, want_g=True)
+        if down is not None:
+            dzd, _ = self._bn_bwd(down, g, None, ACT_NONE)
+            skip = self._conv_bwd(down, dzd)
+        else:
+            skip = g
+        d = self._conv_bwd(last, dz)
+        for u in reversed(units[1:-1]):
+            dz, _ = self._bn_bwd(u, d, u.y, ACT_RELU)
+            d = self._conv_bwd(u, dz)
+        u = units[0]
+        dz, _ = self._bn_bwd(u, d, u.y, ACT_RELU)
+        return self._conv_bwd(u, dz, residual=skip)
+
+    # ---- whole network ------------------------------------------------------------------------------
+    def run_forward(self, x, training, want_tape):
+        h, stem = self._stem_fwd(x, training)
+        saved = []
+        for spec in self.blocks:
+            h, s = self._block_fwd(spec, h, training)
+            saved.append(s if want_tape else None)
+        N = h.shape[0]
+        feat = ops.avgpool_fwd(h)                                        # [N,1,1,C]
+        desc = ops.make_desc(N, 1, 1, self.fc_in, self.classes_pad, 1, 1, 1, 0)
+        logits = ops.conv_fprop(feat, self.fc_w16, desc, bias=self.fc_b, out_fp32=True).view(N, self.classes_pad)
+        out = logits if self.classes_pad == self.classes else logits[:, :self.classes]
+        tape = None
+        if want_tape:
+            tape = {'stem': stem, 'blocks': saved, 'feat': feat, 'last_shape': tuple(h.shape), 'fc_desc': desc}
+        return out, tape
+
+    def run_backward(self, tape, dlogits):
+        N = dlogits.shape[0]
+        if self.classes_pad == self.classes:
+            dl = torch.empty((N, self.classes_pad), device=self.device, dtype=torch.bfloat16)
+            ops.cast_bf16(dlogits.contiguous().float(), dl)
+        else:
+            dl = torch.zeros((N, self.classes_pad), device=self.device, dtype=torch.bfloat16)
+            dl[:, :self.classes].copy_(dlogits)
+        desc = tape['fc_desc']
+        dl4 = dl.view(N, 1, 1, self.classes_pad)
+        ops.colsum_bf16(dl, self.fc_gb)
+        ops.conv_wgrad(tape['feat'], dl4, desc, self.fc_gw)
+        wt = ops.weight_transpose(self.fc_w16)
+        dfeat = ops.conv_dgrad(dl4, wt, desc)
+        d = ops.avgpool_bwd(dfeat, tape['last_shape'])
+        for spec, saved in zip(reversed(self.blocks), reversed(tape['blocks'])):
+            d = self._block_bwd(spec, saved, d)
+        self._stem_bwd(tape['stem'], d)
+
+
+def convert_b200(model, device=None):
+    """Convert a registry model for the B200 kernel path (in place) and return it."""
+    from .models.resnet import ResNet
+    from . import lib
+    lib.load()  # fail loudly when the CUDA extension is missing
+    if not torch.cuda.is_available():
+        raise B200Error('convert_b200 needs a CUDA device: the B200 path has no CPU fallback')
+    device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+    if getattr(model, '_b200', None) is not None:
+        return model
+    if isinstance(model, ResNet):
+        rt = ResNetRuntime(model, device)
+    else:
+        raise B200Error('no B200 runtime for model type %s yet' % type(model).__name__)
+    object.__setattr__(model, '_b200', rt)
+    return model

@@ -1,0 +1,258 @@
+"""Tensor-level wrappers over the C ABI (one Python function per entry point of include/b200conv.h).
+
+Tensors are torch CUDA tensors used purely as device-memory handles: activations are contiguous
+[N,H,W,C] bf16, conv weights [K, R*S, C] bf16, statistics / master weights / gradients fp32.
+Every call is asynchronous on the current torch CUDA stream.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _l
+from .lib import ACT_NONE, ACT_RELU, ACT_RELU6, ConvDesc, Epilogue  # noqa: F401
+
+bf16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _l.B200Error("%s must be a CUDA tensor (no CPU fallback exists)" % name)
+    if t.dtype != dtype:
+        raise _l.B200Error("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _l.B200Error("%s must be contiguous" % name)
+
+
+def out_size(h, r, stride, pad_lo, pad_hi=None):
+    pad_hi = pad_lo if pad_hi is None else pad_hi
+    return (h + pad_lo + pad_hi - r) // stride + 1
+
+
+def make_desc(N, H, W, C, K, R, S, stride, pad, P=None, Q=None):
+    pad_h, pad_w = (pad, pad) if isinstance(pad, int) else pad
+    P = out_size(H, R, stride, pad_h) if P is None else P
+    Q = out_size(W, S, stride, pad_w) if Q is None else Q
+    return ConvDesc(N, H, W, C, K, R, S, stride, pad_h, pad_w, P, Q)
+
+
+# ------------------------------------------------------------------------------------ convolution
+def conv_fprop(x, w, desc, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32=False):
+    """x [N,H,W,C] bf16, w [K,R*S,C] bf16 -> y [N,P,Q,K] (bf16, or fp32 if out_fp32)."""
+    _chk(x, bf16, "x"); _chk(w, bf16, "w"); _chk(bias, torch.float32, "bias"); _chk(residual, bf16, "residual")
+    if out is None:
+        out = torch.empty((desc.N, desc.P, desc.Q, desc.K), device=x.device,
+                          dtype=torch.float32 if out_fp32 else bf16)
+    ep = Epilogue(_l.ptr(bias), _l.ptr(residual), int(act), int(bool(out_fp32)))
+    _l.check(_l.load().b200_conv_fprop(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), out.data_ptr(),
+                                       ctypes.byref(ep), _stream()), "b200_conv_fprop")
+    return out
+
+
+def conv_dgrad(dy, wt, desc, out=None, residual=None):
+    """dy [N,P,Q,K] bf16, wt [C,R*S,K] bf16 -> dx [N,H,W,C] bf16 (+ residual)."""
+    _chk(dy, bf16, "dy"); _chk(wt, bf16, "wt"); _chk(residual, bf16, "residual")
+    if out is None:
+        out = torch.empty((desc.N, desc.H, desc.W, desc.C), device=dy.device, dtype=bf16)
+    _l.check(_l.load().b200_conv_dgrad(ctypes.byref(desc), dy.data_ptr(), wt.data_ptr(), out.data_ptr(),
+                                       _l.ptr(residual), _stream()), "b200_conv_dgrad")
+    return out
+
+
+def conv_wgrad(x, dy, desc, dw):
+    """dw [K,R*S,C] fp32 += dy^T (*) x."""
+    _chk(x, bf16, "x"); _chk(dy, bf16, "dy"); _chk(dw, torch.float32, "dw")
+    _l.check(_l.load().b200_conv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _stream()),
+             "b200_conv_wgrad")
+    return dw
+
+
+def dwconv_fprop(x, w, desc, out=None):
+    _chk(x, bf16, "x"); _chk(w, bf16, "w")
+    if out is None:
+        out = torch.empty((desc.N, desc.P, desc.Q, desc.K), device=x.device, dtype=bf16)
+    _l.check(_l.load().b200_dwconv_fprop(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), out.data_ptr(), _stream()),
+             "b200_dwconv_fprop")
+    return out
+
+
+def dwconv_dgrad(dy, w, desc, out=None):
+    _chk(dy, bf16, "dy"); _chk(w, bf16, "w")
+    if out is None:
+        out = torch.empty((desc.N, desc.H, desc.W, desc.C), device=dy.device, dtype=bf16)
+    _l.check(_l.load().b200_dwconv_dgrad(ctypes.byref(desc), dy.data_ptr(), w.data_ptr(), out.data_ptr(), _stream()),
+             "b200_dwconv_dgrad")
+    return out
+
+
+def dwconv_wgrad(x, dy, desc, dw, workspace):
+    _chk(x, bf16, "x"); _chk(dy, bf16, "dy"); _chk(dw, torch.float32, "dw"); _chk(workspace, torch.float32, "ws")
+    _l.check(_l.load().b200_dwconv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                                         workspace.data_ptr(), workspace.numel() * 4, _stream()), "b200_dwconv_wgrad")
+    return dw
+
+
+# ------------------------------------------------------------------------------------ batch norm
+def bn_workspace_floats(C):
+    return int(_l.load().b200_bn_workspace_floats(int(C)))
+
+
+def bn_stats(z, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd, scale, shift, workspace):
+    C = z.shape[-1]
+    M = z.numel() // C
+    _chk(z, bf16, "z")
+    mom = -1.0 if momentum is None else float(momentum)
+    _l.check(_l.load().b200_bn_stats(z.data_ptr(), M, C, _l.ptr(gamma), _l.ptr(beta), float(eps), mom,
+                                     _l.ptr(running_mean), _l.ptr(running_var), _l.ptr(nbt), mean.data_ptr(),
+                                     invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), workspace.data_ptr(),
+                                     _stream()), "b200_bn_stats")
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, scale, shift):
+    C = running_mean.numel()
+    _l.check(_l.load().b200_bn_eval_coeffs(C, _l.ptr(gamma), _l.ptr(beta), running_mean.data_ptr(),
+                                           running_var.data_ptr(), float(eps), scale.data_ptr(), shift.data_ptr(),
+                                           _stream()), "b200_bn_eval_coeffs")
+
+
+def bn_apply(z, scale, shift, act=ACT_NONE, residual=None, z2=None, scale2=None, shift2=None, out=None):
+    C = z.shape[-1]
+    M = z.numel() // C
+    _chk(z, bf16, "z"); _chk(residual, bf16, "residual"); _chk(z2, bf16, "z2")
+    if out is None:
+        out = torch.empty_like(z)
+    _l.check(_l.load().b200_bn_apply(z.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), _l.ptr(residual),
+                                     _l.ptr(z2), _l.ptr(scale2), _l.ptr(shift2), int(act), out.data_ptr(), _stream()),
+             "b200_bn_apply")
+    return out
+
+
+def bn_bwd_reduce(dy, y, z, act, mean, invstd, sums, dgamma_acc, dbeta_acc, workspace):
+    C = z.shape[-1]
+    M = z.numel() // C
+    _chk(dy, bf16, "dy"); _chk(y, bf16, "y"); _chk(z, bf16, "z")
+    _l.check(_l.load().b200_bn_bwd_reduce(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
+                                          invstd.data_ptr(), sums.data_ptr(), _l.ptr(dgamma_acc), _l.ptr(dbeta_acc),
+                                          workspace.data_ptr(), _stream()), "b200_bn_bwd_reduce")
+
+
+def bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, sums, dz=None, g_out=None):
+    C = z.shape[-1]
+    M = z.numel() // C
+    if dz is None:
+        dz = torch.empty_like(z)
+    _l.check(_l.load().b200_bn_bwd_dx(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
+                                      invstd.data_ptr(), _l.ptr(gamma), sums.data_ptr(), dz.data_ptr(),
+                                      _l.ptr(g_out), _stream()), "b200_bn_bwd_dx")
+    return dz
+
+
+# ------------------------------------------------------------------------------------ pooling
+def maxpool_fwd(x, want_argmax=True):
+    N, H, W, C = x.shape
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((N, OH, OW, C), device=x.device, dtype=bf16)
+    am = torch.empty((N, OH, OW, C), device=x.device, dtype=torch.uint8) if want_argmax else None
+    _l.check(_l.load().b200_maxpool3x3s2_fwd(x.data_ptr(), N, H, W, C, y.data_ptr(), _l.ptr(am), _stream()),
+             "b200_maxpool3x3s2_fwd")
+    return y, am
+
+
+def maxpool_bwd(dy, argmax, in_shape):
+    N, H, W, C = in_shape
+    dx = torch.empty(in_shape, device=dy.device, dtype=bf16)
+    _l.check(_l.load().b200_maxpool3x3s2_bwd(dy.data_ptr(), argmax.data_ptr(), N, H, W, C, dx.data_ptr(), _stream()),
+             "b200_maxpool3x3s2_bwd")
+    return dx
+
+
+def avgpool_fwd(x):
+    N, H, W, C = x.shape
+    y = torch.empty((N, 1, 1, C), device=x.device, dtype=bf16)
+    _l.check(_l.load().b200_avgpool_fwd(x.data_ptr(), N, H * W, C, y.data_ptr(), _stream()), "b200_avgpool_fwd")
+    return y
+
+
+def avgpool_bwd(dy, in_shape):
+    N, H, W, C = in_shape
+    dx = torch.empty(in_shape, device=dy.device, dtype=bf16)
+    _l.check(_l.load().b200_avgpool_bwd(dy.data_ptr(), N, H * W, C, dx.data_ptr(), _stream()), "b200_avgpool_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------ layout / casts
+def input_prep(x_nchw, cpad, s2d=False):
+    """NCHW fp32 -> NHWC bf16 (channels zero-padded to cpad) or its 2x2 space-to-depth form."""
+    _chk(x_nchw, torch.float32, "x")
+    N, C, H, W = x_nchw.shape
+    shape = (N, H // 2, W // 2, cpad) if s2d else (N, H, W, cpad)
+    out = torch.empty(shape, device=x_nchw.device, dtype=bf16)
+    _l.check(_l.load().b200_input_prep(x_nchw.data_ptr(), N, C, H, W, cpad, 1 if s2d else 0, out.data_ptr(),
+                                       _stream()), "b200_input_prep")
+    return out
+
+
+def weight_transpose(w, out=None):
+    """bf16 [K,T,C] -> [C,T,K]."""
+    K, T, C = w.shape
+    if out is None:
+        out = torch.empty((C, T, K), device=w.device, dtype=bf16)
+    _l.check(_l.load().b200_weight_transpose(w.data_ptr(), out.data_ptr(), K, T, C, _stream()),
+             "b200_weight_transpose")
+    return out
+
+
+def stem_weight_to_s2d(w_f32, K, C, cpad, out):
+    _l.check(_l.load().b200_stem_weight_to_s2d(w_f32.data_ptr(), K, C, cpad, out.data_ptr(), _stream()),
+             "b200_stem_weight_to_s2d")
+    return out
+
+
+def stem_wgrad_from_s2d(dw_s2d, K, C, cpad, dw):
+    _l.check(_l.load().b200_stem_wgrad_from_s2d(dw_s2d.data_ptr(), K, C, cpad, dw.data_ptr(), _stream()),
+             "b200_stem_wgrad_from_s2d")
+    return dw
+
+
+def cast_bf16(src, dst):
+    _l.check(_l.load().b200_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()),
+             "b200_cast_f32_to_bf16")
+    return dst
+
+
+# ------------------------------------------------------------------------------------ loss / optimizer
+def softmax_ce(logits, target, classes, smooth_eps, grad_scale, loss, dlogits):
+    B, ld = logits.shape
+    _chk(logits, torch.float32, "logits"); _chk(target, torch.int64, "target")
+    _l.check(_l.load().b200_softmax_ce(logits.data_ptr(), target.data_ptr(), B, int(classes), int(ld), float(smooth_eps or 0.0),
+                                       float(grad_scale), loss.data_ptr(), _l.ptr(dlogits), _stream()),
+             "b200_softmax_ce")
+
+
+def colsum_bf16(m, out):
+    B, K = m.shape
+    _l.check(_l.load().b200_colsum_bf16(m.data_ptr(), B, K, out.data_ptr(), _stream()), "b200_colsum_bf16")
+
+
+def fused_sgd(p32, g32, m32, p16, n, wd_count, lr, momentum, dampening, weight_decay, inv_scale, clip_coef,
+              first_step):
+    _l.check(_l.load().b200_fused_sgd(p32.data_ptr(), g32.data_ptr(), _l.ptr(m32), _l.ptr(p16), int(n),
+                                      int(wd_count), float(lr), float(momentum), float(dampening),
+                                      float(weight_decay), float(inv_scale), _l.ptr(clip_coef), int(bool(first_step)),
+                                      _stream()), "b200_fused_sgd")
+
+
+def sumsq(g, n, out, workspace):
+    _l.check(_l.load().b200_sumsq(g.data_ptr(), int(n), out.data_ptr(), workspace.data_ptr(), _stream()),
+             "b200_sumsq")
+
+
+def grad_coef(sumsq_t, inv_scale, mode, max_norm, momentum, state, coef_out, norm_out):
+    _l.check(_l.load().b200_grad_coef(sumsq_t.data_ptr(), float(inv_scale), int(mode), float(max_norm),
+                                      float(momentum), _l.ptr(state), coef_out.data_ptr(), _l.ptr(norm_out),
+                                      _stream()), "b200_grad_coef")

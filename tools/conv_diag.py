@@ -1,0 +1,110 @@
+"""GPU diagnostic for the tcgen05 convolution kernels: runs ONE case (argv[1]) or lists cases.
+
+Each case compares fprop / dgrad / wgrad of libb200conv.so with an fp64 torch reference computed on
+bf16-rounded operands.  Driven case-by-case from tools/run_gpu_diag.sh so that a trapped kernel (sticky
+CUDA error) only takes down its own process.
+"""
+import sys
+import os
+import json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+
+# name: (N,H,W,C,K,R,S,stride,pad, extras)
+CASES = {
+    "p1_64_64_m128": (2, 8, 8, 64, 64, 1, 1, 1, 0, {}),
+    "p1_128_256": (2, 8, 8, 128, 256, 1, 1, 1, 0, {}),
+    "p1_256_64_odd": (3, 7, 7, 256, 64, 1, 1, 1, 0, {}),
+    "c3_64_64": (2, 8, 8, 64, 64, 3, 3, 1, 1, {}),
+    "c3s2_64_128": (2, 16, 16, 64, 128, 3, 3, 2, 1, {}),
+    "c3_16_16": (4, 32, 32, 16, 16, 3, 3, 1, 1, {}),
+    "c3s2_16_32": (4, 32, 32, 16, 32, 3, 3, 2, 1, {}),
+    "c3_32_32": (4, 16, 16, 32, 32, 3, 3, 1, 1, {}),
+    "p1s2_16_32": (4, 32, 32, 16, 32, 1, 1, 2, 0, {}),
+    "p1s2_256_512": (4, 28, 28, 256, 512, 1, 1, 2, 0, {}),
+    "c3_64_64_56": (8, 56, 56, 64, 64, 3, 3, 1, 1, {}),
+    "p1_64_256_56": (8, 56, 56, 64, 256, 1, 1, 1, 0, {}),
+    "p1_1024_256_14": (8, 14, 14, 1024, 256, 1, 1, 1, 0, {}),
+    "p1_512_2048_7": (8, 7, 7, 512, 2048, 1, 1, 1, 0, {}),
+    "c3_512_512_7": (8, 7, 7, 512, 512, 3, 3, 1, 1, {}),
+    "c3s2_128_128_56": (4, 56, 56, 128, 128, 3, 3, 2, 1, {}),
+    "fc_2048_1000": (64, 1, 1, 2048, 1000, 1, 1, 1, 0, {"bias": True, "out_fp32": True}),
+    "fc_64_16": (64, 1, 1, 64, 16, 1, 1, 1, 0, {"bias": True, "out_fp32": True}),
+    "stem_s2d": (2, 112, 112, 16, 64, 4, 4, 1, 2, {"P": 112, "Q": 112, "no_dgrad": True}),
+    "mb_24_144": (2, 56, 56, 24, 144, 1, 1, 1, 0, {}),
+    "mb_144_24": (2, 56, 56, 144, 24, 1, 1, 1, 0, {}),
+    "res_relu": (2, 8, 8, 64, 64, 3, 3, 1, 1, {"residual": True, "act": 1}),
+}
+
+
+def rel_err(a, b):
+    a = a.double(); b = b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30)), float((a - b).abs().max()), float(b.abs().max())
+
+
+def run(name):
+    from convnet.pytorch_b200 import ops
+    N, H, W, C, K, R, S, stride, pad, ex = CASES[name]
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = torch.randn(N, H, W, C, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(K, R * S, C, generator=g) / (R * S * C) ** 0.5).to(dev).to(torch.bfloat16)
+    P = ex.get("P"); Q = ex.get("Q")
+    desc = ops.make_desc(N, H, W, C, K, R, S, stride, pad, P, Q)
+    P, Q = desc.P, desc.Q
+    pad_hi_h = (P - 1) * stride + R - H - pad
+    pad_hi_w = (Q - 1) * stride + S - W - pad
+    # references in fp64, NCHW
+    xd = x.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wd = w.double().view(K, R, S, C).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    xp = F.pad(xd, (pad, pad_hi_w, pad, pad_hi_h))
+    bias = torch.randn(K, generator=g).to(dev) if ex.get("bias") else None
+    yref = F.conv2d(xp, wd, bias.double() if bias is not None else None, stride=stride)
+    res = None
+    if ex.get("residual"):
+        res = torch.randn(N, P, Q, K, generator=g).to(dev).to(torch.bfloat16)
+        yref = yref + res.double().permute(0, 3, 1, 2)
+    if ex.get("act") == 1:
+        yref = yref.relu()
+    out = {"case": name}
+    y = ops.conv_fprop(x, w, desc, bias=bias, residual=res, act=ex.get("act", 0), out_fp32=ex.get("out_fp32", False))
+    torch.cuda.synchronize()
+    out["fprop"] = rel_err(y.permute(0, 3, 1, 2), yref.detach())
+    # backward
+    dy = torch.randn(N, P, Q, K, generator=g).to(dev).to(torch.bfloat16)
+    yplain = F.conv2d(xp, wd, None, stride=stride)
+    gx, gw = torch.autograd.grad(yplain, [xd, wd], dy.double().permute(0, 3, 1, 2))
+    if not ex.get("no_dgrad"):
+        wt = ops.weight_transpose(w)
+        torch.cuda.synchronize()
+        wt_ref = w.permute(2, 1, 0).contiguous()
+        out["transpose_ok"] = bool(torch.equal(wt, wt_ref))
+        dx = ops.conv_dgrad(dy, wt, desc)
+        torch.cuda.synchronize()
+        out["dgrad"] = rel_err(dx.permute(0, 3, 1, 2), gx)
+    dw = torch.zeros(K, R * S, C, device=dev, dtype=torch.float32)
+    ops.conv_wgrad(x, dy, desc, dw)
+    torch.cuda.synchronize()
+    gw_krsc = gw.permute(0, 2, 3, 1).reshape(K, R * S, C)
+    out["wgrad"] = rel_err(dw, gw_krsc)
+    # accumulate semantics
+    ops.conv_wgrad(x, dy, desc, dw)
+    torch.cuda.synchronize()
+    out["wgrad_acc"] = rel_err(dw, 2 * gw_krsc)
+    return out
+
+
+if __name__ == "__main__":
+    if len(sys.argv) < 2:
+        print("\n".join(CASES))
+    else:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            r = run(sys.argv[1])
+            ok = all(v[0] < 1e-2 for k, v in r.items() if isinstance(v, tuple))
+            r["ok"] = ok
+            print("DIAG " + json.dumps(r))
+        except Exception as e:  # noqa
+            print("DIAG " + json.dumps({"case": sys.argv[1], "ok": False, "error": repr(e)[:500]}))
