@@ -460,4 +460,6 @@ def convert_b200(model, device=None):
     else:
         raise B200Error('no B200 runtime for model type %s yet' % type(model).__name__)
     object.__setattr__(model, '_b200', rt)
+    # checkpoints load into the fp32 masters (arena views); refresh the bf16 compute shadow afterwards
+    model.register_load_state_dict_post_hook(lambda module, incompatible: rt.arena.sync_shadow())
     return model

@@ -18,6 +18,54 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- optional per-call device timing (bench.py's kernel-class breakdown): CUDA events on the launch stream
+_TIMING = None
+
+
+class _T(object):
+    __slots__ = ('name', 'flops', 'nbytes', 'e0')
+
+    def __init__(self, name, flops=0, nbytes=0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _TIMING.append((self.name, self.flops, self.nbytes, self.e0, e1))
+        return False
+
+
+def start_timing():
+    global _TIMING
+    _TIMING = []
+
+
+def stop_timing():
+    """-> {class: {'ms', 'calls', 'flops', 'bytes'}} for the calls since start_timing()."""
+    global _TIMING
+    rec, _TIMING = _TIMING, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, flops, nbytes, e0, e1 in rec or []:
+        c = out.setdefault(name, {'ms': 0.0, 'calls': 0, 'flops': 0, 'bytes': 0})
+        c['ms'] += e0.elapsed_time(e1)
+        c['calls'] += 1
+        c['flops'] += flops
+        c['bytes'] += nbytes
+    return out
+
+
+def _conv_flops(d):
+    return 2 * d.N * d.P * d.Q * d.K * d.R * d.S * d.C
+
+
 def _chk(t, dtype, name):
     if t is None:
         return
@@ -49,8 +97,9 @@ def conv_fprop(x, w, desc, out=None, bias=None, residual=None, act=ACT_NONE, out
         out = torch.empty((desc.N, desc.P, desc.Q, desc.K), device=x.device,
                           dtype=torch.float32 if out_fp32 else bf16)
     ep = Epilogue(_l.ptr(bias), _l.ptr(residual), int(act), int(bool(out_fp32)))
-    _l.check(_l.load().b200_conv_fprop(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), out.data_ptr(),
-                                       ctypes.byref(ep), _stream()), "b200_conv_fprop")
+    with _T('conv_fprop', _conv_flops(desc), 0):
+        _l.check(_l.load().b200_conv_fprop(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), out.data_ptr(),
+                                           ctypes.byref(ep), _stream()), "b200_conv_fprop")
     return out
 
 
@@ -59,16 +108,18 @@ def conv_dgrad(dy, wt, desc, out=None, residual=None):
     _chk(dy, bf16, "dy"); _chk(wt, bf16, "wt"); _chk(residual, bf16, "residual")
     if out is None:
         out = torch.empty((desc.N, desc.H, desc.W, desc.C), device=dy.device, dtype=bf16)
-    _l.check(_l.load().b200_conv_dgrad(ctypes.byref(desc), dy.data_ptr(), wt.data_ptr(), out.data_ptr(),
-                                       _l.ptr(residual), _stream()), "b200_conv_dgrad")
+    with _T('conv_dgrad', _conv_flops(desc), 0):
+        _l.check(_l.load().b200_conv_dgrad(ctypes.byref(desc), dy.data_ptr(), wt.data_ptr(), out.data_ptr(),
+                                           _l.ptr(residual), _stream()), "b200_conv_dgrad")
     return out
 
 
 def conv_wgrad(x, dy, desc, dw):
     """dw [K,R*S,C] fp32 += dy^T (*) x."""
     _chk(x, bf16, "x"); _chk(dy, bf16, "dy"); _chk(dw, torch.float32, "dw")
-    _l.check(_l.load().b200_conv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _stream()),
-             "b200_conv_wgrad")
+    with _T('conv_wgrad', _conv_flops(desc), 0):
+        _l.check(_l.load().b200_conv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _stream()),
+                 "b200_conv_wgrad")
     return dw
 
 
@@ -107,10 +158,11 @@ def bn_stats(z, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean
     M = z.numel() // C
     _chk(z, bf16, "z")
     mom = -1.0 if momentum is None else float(momentum)
-    _l.check(_l.load().b200_bn_stats(z.data_ptr(), M, C, _l.ptr(gamma), _l.ptr(beta), float(eps), mom,
-                                     _l.ptr(running_mean), _l.ptr(running_var), _l.ptr(nbt), mean.data_ptr(),
-                                     invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), workspace.data_ptr(),
-                                     _stream()), "b200_bn_stats")
+    with _T('bn_stats', 0, 2 * z.numel()):
+        _l.check(_l.load().b200_bn_stats(z.data_ptr(), M, C, _l.ptr(gamma), _l.ptr(beta), float(eps), mom,
+                                         _l.ptr(running_mean), _l.ptr(running_var), _l.ptr(nbt), mean.data_ptr(),
+                                         invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), workspace.data_ptr(),
+                                         _stream()), "b200_bn_stats")
 
 
 def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, scale, shift):
@@ -126,9 +178,10 @@ def bn_apply(z, scale, shift, act=ACT_NONE, residual=None, z2=None, scale2=None,
     _chk(z, bf16, "z"); _chk(residual, bf16, "residual"); _chk(z2, bf16, "z2")
     if out is None:
         out = torch.empty_like(z)
-    _l.check(_l.load().b200_bn_apply(z.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), _l.ptr(residual),
-                                     _l.ptr(z2), _l.ptr(scale2), _l.ptr(shift2), int(act), out.data_ptr(), _stream()),
-             "b200_bn_apply")
+    with _T('bn_apply', 0, 2 * z.numel() * (2 + (residual is not None) + (z2 is not None))):
+        _l.check(_l.load().b200_bn_apply(z.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), _l.ptr(residual),
+                                         _l.ptr(z2), _l.ptr(scale2), _l.ptr(shift2), int(act), out.data_ptr(), _stream()),
+                 "b200_bn_apply")
     return out
 
 
@@ -136,9 +189,10 @@ def bn_bwd_reduce(dy, y, z, act, mean, invstd, sums, dgamma_acc, dbeta_acc, work
     C = z.shape[-1]
     M = z.numel() // C
     _chk(dy, bf16, "dy"); _chk(y, bf16, "y"); _chk(z, bf16, "z")
-    _l.check(_l.load().b200_bn_bwd_reduce(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
-                                          invstd.data_ptr(), sums.data_ptr(), _l.ptr(dgamma_acc), _l.ptr(dbeta_acc),
-                                          workspace.data_ptr(), _stream()), "b200_bn_bwd_reduce")
+    with _T('bn_bwd_reduce', 0, 2 * z.numel() * (2 + (y is not None))):
+        _l.check(_l.load().b200_bn_bwd_reduce(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
+                                              invstd.data_ptr(), sums.data_ptr(), _l.ptr(dgamma_acc), _l.ptr(dbeta_acc),
+                                              workspace.data_ptr(), _stream()), "b200_bn_bwd_reduce")
 
 
 def bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, sums, dz=None, g_out=None):
@@ -146,9 +200,10 @@ def bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, sums, dz=None, g_out=None):
     M = z.numel() // C
     if dz is None:
         dz = torch.empty_like(z)
-    _l.check(_l.load().b200_bn_bwd_dx(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
-                                      invstd.data_ptr(), _l.ptr(gamma), sums.data_ptr(), dz.data_ptr(),
-                                      _l.ptr(g_out), _stream()), "b200_bn_bwd_dx")
+    with _T('bn_bwd_dx', 0, 2 * z.numel() * (3 + (y is not None) + (g_out is not None))):
+        _l.check(_l.load().b200_bn_bwd_dx(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
+                                          invstd.data_ptr(), _l.ptr(gamma), sums.data_ptr(), dz.data_ptr(),
+                                          _l.ptr(g_out), _stream()), "b200_bn_bwd_dx")
     return dz
 
 
@@ -158,30 +213,34 @@ def maxpool_fwd(x, want_argmax=True):
     OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty((N, OH, OW, C), device=x.device, dtype=bf16)
     am = torch.empty((N, OH, OW, C), device=x.device, dtype=torch.uint8) if want_argmax else None
-    _l.check(_l.load().b200_maxpool3x3s2_fwd(x.data_ptr(), N, H, W, C, y.data_ptr(), _l.ptr(am), _stream()),
-             "b200_maxpool3x3s2_fwd")
+    with _T('maxpool_fwd', 0, 2 * x.numel() + 3 * y.numel()):
+        _l.check(_l.load().b200_maxpool3x3s2_fwd(x.data_ptr(), N, H, W, C, y.data_ptr(), _l.ptr(am), _stream()),
+                 "b200_maxpool3x3s2_fwd")
     return y, am
 
 
 def maxpool_bwd(dy, argmax, in_shape):
     N, H, W, C = in_shape
     dx = torch.empty(in_shape, device=dy.device, dtype=bf16)
-    _l.check(_l.load().b200_maxpool3x3s2_bwd(dy.data_ptr(), argmax.data_ptr(), N, H, W, C, dx.data_ptr(), _stream()),
-             "b200_maxpool3x3s2_bwd")
+    with _T('maxpool_bwd', 0, 2 * dx.numel() + 3 * dy.numel()):
+        _l.check(_l.load().b200_maxpool3x3s2_bwd(dy.data_ptr(), argmax.data_ptr(), N, H, W, C, dx.data_ptr(), _stream()),
+                 "b200_maxpool3x3s2_bwd")
     return dx
 
 
 def avgpool_fwd(x):
     N, H, W, C = x.shape
     y = torch.empty((N, 1, 1, C), device=x.device, dtype=bf16)
-    _l.check(_l.load().b200_avgpool_fwd(x.data_ptr(), N, H * W, C, y.data_ptr(), _stream()), "b200_avgpool_fwd")
+    with _T('avgpool', 0, 2 * x.numel()):
+        _l.check(_l.load().b200_avgpool_fwd(x.data_ptr(), N, H * W, C, y.data_ptr(), _stream()), "b200_avgpool_fwd")
     return y
 
 
 def avgpool_bwd(dy, in_shape):
     N, H, W, C = in_shape
     dx = torch.empty(in_shape, device=dy.device, dtype=bf16)
-    _l.check(_l.load().b200_avgpool_bwd(dy.data_ptr(), N, H * W, C, dx.data_ptr(), _stream()), "b200_avgpool_bwd")
+    with _T('avgpool', 0, 2 * dx.numel()):
+        _l.check(_l.load().b200_avgpool_bwd(dy.data_ptr(), N, H * W, C, dx.data_ptr(), _stream()), "b200_avgpool_bwd")
     return dx
 
 
@@ -192,8 +251,9 @@ def input_prep(x_nchw, cpad, s2d=False):
     N, C, H, W = x_nchw.shape
     shape = (N, H // 2, W // 2, cpad) if s2d else (N, H, W, cpad)
     out = torch.empty(shape, device=x_nchw.device, dtype=bf16)
-    _l.check(_l.load().b200_input_prep(x_nchw.data_ptr(), N, C, H, W, cpad, 1 if s2d else 0, out.data_ptr(),
-                                       _stream()), "b200_input_prep")
+    with _T('input_prep', 0, 4 * x_nchw.numel() + 2 * out.numel()):
+        _l.check(_l.load().b200_input_prep(x_nchw.data_ptr(), N, C, H, W, cpad, 1 if s2d else 0, out.data_ptr(),
+                                           _stream()), "b200_input_prep")
     return out
 
 
@@ -202,8 +262,9 @@ def weight_transpose(w, out=None):
     K, T, C = w.shape
     if out is None:
         out = torch.empty((C, T, K), device=w.device, dtype=bf16)
-    _l.check(_l.load().b200_weight_transpose(w.data_ptr(), out.data_ptr(), K, T, C, _stream()),
-             "b200_weight_transpose")
+    with _T('weight_transpose', 0, 4 * w.numel()):
+        _l.check(_l.load().b200_weight_transpose(w.data_ptr(), out.data_ptr(), K, T, C, _stream()),
+                 "b200_weight_transpose")
     return out
 
 
@@ -220,8 +281,9 @@ def stem_wgrad_from_s2d(dw_s2d, K, C, cpad, dw):
 
 
 def cast_bf16(src, dst):
-    _l.check(_l.load().b200_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()),
-             "b200_cast_f32_to_bf16")
+    with _T('cast', 0, 6 * src.numel()):
+        _l.check(_l.load().b200_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()),
+                 "b200_cast_f32_to_bf16")
     return dst
 
 
@@ -241,10 +303,11 @@ def colsum_bf16(m, out):
 
 def fused_sgd(p32, g32, m32, p16, n, wd_count, lr, momentum, dampening, weight_decay, inv_scale, clip_coef,
               first_step):
-    _l.check(_l.load().b200_fused_sgd(p32.data_ptr(), g32.data_ptr(), _l.ptr(m32), _l.ptr(p16), int(n),
-                                      int(wd_count), float(lr), float(momentum), float(dampening),
-                                      float(weight_decay), float(inv_scale), _l.ptr(clip_coef), int(bool(first_step)),
-                                      _stream()), "b200_fused_sgd")
+    with _T('fused_sgd', 0, 22 * int(n)):
+        _l.check(_l.load().b200_fused_sgd(p32.data_ptr(), g32.data_ptr(), _l.ptr(m32), _l.ptr(p16), int(n),
+                                          int(wd_count), float(lr), float(momentum), float(dampening),
+                                          float(weight_decay), float(inv_scale), _l.ptr(clip_coef), int(bool(first_step)),
+                                          _stream()), "b200_fused_sgd")
 
 
 def sumsq(g, n, out, workspace):

@@ -1,0 +1,258 @@
+"""Training / evaluation loop with the reference's ``Trainer`` interface (trainer.py:54-285).
+
+    Trainer(model, criterion, optimizer=None, device_ids=[0], device='cuda', dtype=torch.float,
+            distributed=False, local_rank=-1, adapt_grad_norm=None, mixup=None, cutmix=None,
+            loss_scale=1., grad_clip=-1, print_freq=100)
+    .train(loader, average_output=False, chunk_batch=1) / .validate(loader) / .calibrate_bn(loader, num_steps)
+        -> dict of meter averages (step, data, loss, prec1, prec5, error1, error5[, grad])
+
+One iteration = zero_grad -> regime update -> H2D -> forward -> loss -> backward -> unscale -> clip ->
+optimizer step, as in ``Trainer._step`` (trainer.py:106-177).
+
+B200 path (model converted by engine.convert_b200): inputs stay fp32 NCHW on the device (the stem kernel
+does the bf16/NHWC conversion), gradients land in the flat arena, the data-parallel reduction is ONE
+NCCL all-reduce of that arena (no DistributedDataParallel wrapper, no per-forward buffer broadcast --
+SURVEY.md section 2.3 C1/C2), and the per-tensor unscale / clip loops of the reference
+(trainer.py:165-172) are folded into the fused optimizer kernel.
+"""
+import logging
+import time
+
+import torch
+import torch.nn as nn
+import torch.distributed as dist
+from torch.nn.utils import clip_grad_norm_
+
+from .utils.meters import AverageMeter, accuracy
+
+_METERS = ('step', 'data', 'loss', 'prec1', 'prec5')
+
+
+def _flatten_duplicates(inputs, target, batch_first=True, expand_target=True):
+    """[B, D, C, H, W] batch-augmentation input -> [(B*D), C, H, W]; targets repeated to match."""
+    copies = inputs.size(1)
+    if not batch_first:
+        inputs = inputs.transpose(0, 1)
+    inputs = inputs.flatten(0, 1)
+    if expand_target:
+        if batch_first:
+            target = target.view(-1, 1).expand(-1, copies)
+        else:
+            target = target.view(1, -1).expand(copies, -1)
+        target = target.flatten(0, 1)
+    return inputs, target
+
+
+def _average_duplicates(outputs, target, batch_first=True):
+    """Mean of the network outputs over the duplicates of each sample (target is NOT expanded)."""
+    bsz = target.size(0)
+    if batch_first:
+        return outputs.view(bsz, -1, *outputs.shape[1:]).mean(dim=1)
+    return outputs.view(-1, bsz, *outputs.shape[1:]).mean(dim=0)
+
+
+class Trainer(object):
+    def __init__(self, model, criterion, optimizer=None, device_ids=[0], device='cuda', dtype=torch.float,
+                 distributed=False, local_rank=-1, adapt_grad_norm=None, mixup=None, cutmix=None,
+                 loss_scale=1., grad_clip=-1, print_freq=100):
+        if mixup is not None or cutmix is not None:
+            raise NotImplementedError('mixup / cutmix are outside the B200 hot path (SURVEY.md section 2, #18)')
+        self._model = model
+        self.criterion = criterion
+        self.epoch = 0
+        self.training_steps = 0
+        self.optimizer = optimizer
+        self.device = device
+        self.dtype = dtype
+        self.distributed = distributed
+        self.local_rank = local_rank
+        self.print_freq = print_freq
+        self.grad_clip = grad_clip
+        self.grad_scale = None
+        self.loss_scale = loss_scale
+        self.adapt_grad_norm = adapt_grad_norm
+        self.b200 = getattr(model, '_b200', None)
+        self.world_size = dist.get_world_size() if (distributed and dist.is_initialized()) else 1
+
+        if self.b200 is not None:
+            self.model = model
+            if distributed and self.world_size > 1:
+                self._broadcast_initial_state()
+        elif distributed:
+            if device_ids and 'cuda' in str(device):
+                self.model = nn.parallel.DistributedDataParallel(model, device_ids=device_ids,
+                                                                 output_device=device_ids[0])
+            else:  # CPU / gloo processes (the reference crashes here: trainer.py:82 with device_ids=None)
+                self.model = nn.parallel.DistributedDataParallel(model)
+        elif device_ids and len(device_ids) > 1:
+            self.model = nn.DataParallel(model, device_ids)
+        else:
+            self.model = model
+
+    # ------------------------------------------------------------------ data-parallel helpers (B200)
+    def _broadcast_initial_state(self):
+        """rank 0 -> all: parameters (one flat broadcast) and BN buffers, once (what DDP's ctor does)."""
+        arena = self.b200.arena
+        dist.broadcast(arena.p32, src=0)
+        for buf in self._model.buffers():
+            dist.broadcast(buf, src=0)
+        arena.sync_shadow()
+
+    def _allreduce_gradients(self):
+        if self.b200 is not None and self.world_size > 1:
+            dist.all_reduce(self.b200.arena.g32)  # sum; the 1/world factor is folded into the SGD kernel
+
+    # ------------------------------------------------------------------ one optimisation step
+    def _input_dtype(self):
+        return torch.float if self.b200 is not None else self.dtype
+
+    def _grad_norm(self, inputs_batch, target_batch, chunk_batch=1):
+        self.model.zero_grad()
+        for inputs, target in zip(inputs_batch.chunk(chunk_batch, dim=0), target_batch.chunk(chunk_batch, dim=0)):
+            target = target.to(self.device)
+            inputs = inputs.to(self.device, dtype=self._input_dtype())
+            loss = self.criterion(self.model(inputs), target)
+            if chunk_batch > 1:
+                loss = loss / chunk_batch
+            loss.backward()
+        return clip_grad_norm_(self.model.parameters(), float('inf'))
+
+    def _step(self, inputs_batch, target_batch, training=False, average_output=False, chunk_batch=1):
+        outputs, total_loss, grad = [], 0, None
+        if training:
+            self.optimizer.zero_grad()
+            self.optimizer.update(self.epoch, self.training_steps)
+
+        chunks = zip(inputs_batch.chunk(chunk_batch, dim=0), target_batch.chunk(chunk_batch, dim=0))
+        for i, (inputs, target) in enumerate(chunks):
+            target = target.to(self.device, non_blocking=True)
+            inputs = inputs.to(self.device, dtype=self._input_dtype(), non_blocking=True)
+            if training:
+                self.optimizer.pre_forward()
+            output = self.model(inputs)
+            if average_output:
+                if isinstance(output, (list, tuple)):
+                    output = [_average_duplicates(o, target) if o is not None else None for o in output]
+                else:
+                    output = _average_duplicates(output, target)
+            loss = self.criterion(output, target)
+            if chunk_batch > 1:
+                loss = loss / chunk_batch
+            if isinstance(output, (list, tuple)):
+                output = output[0]
+            outputs.append(output.detach())
+            total_loss += float(loss.detach())
+
+            if training:
+                if i == 0:
+                    self.optimizer.pre_backward()
+                if self.grad_scale is not None:
+                    loss = loss * self.grad_scale
+                if self.loss_scale is not None:
+                    loss = loss * self.loss_scale
+                loss.backward()
+
+        if training:
+            if self.b200 is not None:
+                self._allreduce_gradients()
+                self.optimizer.set_grad_unscale(self.loss_scale if self.loss_scale is not None else 1.0,
+                                                self.world_size)
+                if self.grad_clip > 0:
+                    self.optimizer.request_clip(self.grad_clip)
+                self.optimizer.step()
+                if self.grad_clip > 0:
+                    grad = self.optimizer.last_grad_norm
+            else:
+                if self.loss_scale is not None:
+                    for p in self.model.parameters():
+                        if p.grad is not None:
+                            p.grad.data.div_(self.loss_scale)
+                if self.grad_clip > 0:
+                    grad = clip_grad_norm_(self.model.parameters(), self.grad_clip)
+                self.optimizer.step()
+            self.training_steps += 1
+
+        return torch.cat(outputs, dim=0), total_loss, grad
+
+    # ------------------------------------------------------------------ epoch loop
+    def forward(self, data_loader, num_steps=None, training=False, average_output=False, chunk_batch=1):
+        meters = {name: AverageMeter() for name in _METERS}
+        if training and self.grad_clip > 0:
+            meters['grad'] = AverageMeter()
+        batch_first = not ((training and isinstance(self.model, nn.DataParallel)) or chunk_batch > 1)
+
+        def summary():
+            res = {name: m.avg for name, m in meters.items()}
+            res['error1'] = 100. - res['prec1']
+            res['error5'] = 100. - res['prec5']
+            return res
+
+        try:
+            n_batches = len(data_loader)
+        except TypeError:
+            n_batches = -1
+        tick = time.time()
+        for i, (inputs, target) in enumerate(data_loader):
+            duplicates = inputs.dim() > 4  # B x D x C x H x W
+            if training and duplicates and self.adapt_grad_norm is not None and i % self.adapt_grad_norm == 0:
+                per_copy = sum(float(self._grad_norm(inputs.select(1, j), target)) for j in range(inputs.size(1)))
+                per_copy /= inputs.size(1)
+                joint = float(self._grad_norm(*_flatten_duplicates(inputs, target, batch_first)))
+                self.grad_scale = per_copy / joint
+                logging.info('New loss scale: %s', self.grad_scale)
+
+            meters['data'].update(time.time() - tick)
+            if duplicates:
+                inputs, target = _flatten_duplicates(inputs, target, batch_first,
+                                                     expand_target=not average_output)
+            output, loss, grad = self._step(inputs, target, training=training, average_output=average_output,
+                                            chunk_batch=chunk_batch)
+            target_dev = target.to(output.device)
+            prec1, prec5 = accuracy(output, target_dev, topk=(1, 5))
+            n = inputs.size(0)
+            meters['loss'].update(float(loss), n)
+            meters['prec1'].update(float(prec1), n)
+            meters['prec5'].update(float(prec5), n)
+            if grad is not None:
+                meters['grad'].update(float(grad), n)
+            meters['step'].update(time.time() - tick)
+            tick = time.time()
+
+            if i % self.print_freq == 0 or i == n_batches - 1:
+                msg = ('{phase} - Epoch: [{0}][{1}/{2}]\t'
+                       'Time {m[step].val:.3f} ({m[step].avg:.3f})\t'
+                       'Data {m[data].val:.3f} ({m[data].avg:.3f})\t'
+                       'Loss {m[loss].val:.4f} ({m[loss].avg:.4f})\t'
+                       'Prec@1 {m[prec1].val:.3f} ({m[prec1].avg:.3f})\t'
+                       'Prec@5 {m[prec5].val:.3f} ({m[prec5].avg:.3f})\t').format(
+                    self.epoch, i, n_batches, phase='TRAINING' if training else 'EVALUATING', m=meters)
+                if 'grad' in meters:
+                    msg += 'Grad {m[grad].val:.3f} ({m[grad].avg:.3f})'.format(m=meters)
+                logging.info(msg)
+            if num_steps is not None and i >= num_steps:  # (sic) the reference runs num_steps+1 iterations
+                break
+        return summary()
+
+    def train(self, data_loader, average_output=False, chunk_batch=1):
+        self.model.train()
+        return self.forward(data_loader, training=True, average_output=average_output, chunk_batch=chunk_batch)
+
+    def validate(self, data_loader, average_output=False):
+        self.model.eval()
+        with torch.no_grad():
+            return self.forward(data_loader, average_output=average_output, training=False)
+
+    def calibrate_bn(self, data_loader, num_steps=None):
+        """Re-estimate BN running statistics as a cumulative average over the loader (momentum=None)."""
+        for m in self.model.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m.momentum = None
+                m.track_running_stats = True
+                m.reset_running_stats()
+        self.model.train()
+        with torch.no_grad():
+            return self.forward(data_loader, num_steps=num_steps, training=False)
+
+    # tensorwatch hooks of the reference (trainer.py:287-337) are observability extras, not part of the path
+    def set_watcher(self, filename, port=0):
+        return False

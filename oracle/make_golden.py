@@ -1,0 +1,164 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference (read-only at /root/reference) in this
+container.  Run once from the repo root:  python oracle/make_golden.py
+The fixtures pin (a) the oracle restatement (oracle/ref_model.py), (b) the re-authored host code
+(models, regimes, trainer) and (c) -- through the GPU tests -- the CUDA pipeline.
+Nothing here is needed at test time: tests read only the committed fixtures.
+"""
+import json
+import os
+import sys
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+REF = os.environ.get('B200_REFERENCE', '/root/reference')
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    import models as ref_models            # noqa: E402
+    import trainer as ref_trainer          # noqa: E402
+    from utils import optim as ref_optim   # noqa: E402
+    from utils import cross_entropy as ref_ce  # noqa: E402
+    return ref_models, ref_trainer, ref_optim, ref_ce
+
+
+def tensor_stats(sd):
+    out = {}
+    for k, v in sd.items():
+        v = v.double().flatten()
+        out[k] = {'shape': list(sd[k].shape), 'sum': float(v.sum()), 'abs': float(v.abs().sum()),
+                  'head': [float(t) for t in v[:4]]}
+    return out
+
+
+def synth(batch, shape, classes, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, *shape, generator=g), torch.randint(0, classes, (batch,), generator=g)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    ref_models, ref_trainer, ref_optim, ref_ce = import_reference()
+
+    # ---- 1. initialisation of the four model families under the CLI seed (main.py:114-115,137) ----
+    init = {}
+    for name, factory, cfg in [('resnet20_cifar10', ref_models.resnet, dict(dataset='cifar10', depth=20)),
+                               ('resnet50_imagenet', ref_models.resnet, dict(dataset='imagenet', depth=50)),
+                               ('resnext101_imagenet', ref_models.resnext, dict(dataset='imagenet', depth=101)),
+                               ('mobilenet_v2', ref_models.mobilenet_v2, dict(dataset='imagenet'))]:
+        torch.manual_seed(123)
+        m = factory(**cfg)
+        init[name] = {'stats': tensor_stats(m.state_dict()),
+                      'n_params': sum(p.numel() for p in m.parameters())}
+        if hasattr(m, 'regime'):
+            init[name]['regime'] = [{k: (v if isinstance(v, (int, float, str)) else str(type(v).__name__))
+                                     for k, v in ph.items()} for ph in m.regime]
+    with open(os.path.join(OUT, 'init_stats.json'), 'w') as f:
+        json.dump(init, f)
+
+    # ---- 2. resnet20: reference Trainer + OptimRegime, 5 warm-up steps then one recorded step ----
+    torch.manual_seed(123)
+    model = ref_models.resnet(dataset='cifar10', depth=20)
+    x, y = synth(8, (3, 32, 32), 10)
+    crit = ref_ce.CrossEntropyLoss()
+    opt = ref_optim.OptimRegime(model, model.regime)
+    tr = ref_trainer.Trainer(model, crit, opt, device_ids=None, device='cpu', dtype=torch.float, print_freq=1000)
+    model.train()
+    losses = []
+    for _ in range(5):
+        _, loss, _ = tr._step(x, y, training=True)
+        losses.append(float(loss))
+    state_b = deepcopy(model.state_dict())
+    mom_b = {n: opt.optimizer.state[p]['momentum_buffer'].clone() for n, p in model.named_parameters()}
+    # recorded step: capture grads before the optimizer touches them
+    opt.zero_grad(); opt.update(0, tr.training_steps)
+    out = model(x); loss = crit(out, y); loss.backward()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad.data.div_(1.0)
+    opt.step()
+    post = deepcopy(model.state_dict())
+    blob = {'x': x.numpy(), 'y': y.numpy(), 'logits': out.detach().numpy(), 'loss': np.float64(float(loss)),
+            'warm_losses': np.array(losses)}
+    for k, v in state_b.items():
+        blob['state/' + k] = v.numpy()
+    for k, v in mom_b.items():
+        blob['mom/' + k] = v.numpy()
+    for k, v in grads.items():
+        blob['grad/' + k] = v.numpy()
+    for k, v in post.items():
+        blob['post/' + k] = v.numpy()
+    np.savez(os.path.join(OUT, 'resnet20_step.npz'), **blob)
+
+    # ---- 3. reference Trainer.train loop over a tiny loader (loop-level golden) ----
+    torch.manual_seed(123)
+    model = ref_models.resnet(dataset='cifar10', depth=20)
+    opt = ref_optim.OptimRegime(model, model.regime)
+    tr = ref_trainer.Trainer(model, ref_ce.CrossEntropyLoss(), opt, device_ids=None, device='cpu',
+                             dtype=torch.float, print_freq=1000)
+    g = torch.Generator().manual_seed(7)
+    batches = [(torch.randn(16, 3, 32, 32, generator=g), torch.randint(0, 10, (16,), generator=g)) for _ in range(4)]
+    res = tr.train(batches)
+    val = tr.validate(batches[:2])
+    loop = {'train': {k: float(v) for k, v in res.items() if k in ('loss', 'prec1', 'prec5', 'error1', 'error5')},
+            'val': {k: float(v) for k, v in val.items() if k in ('loss', 'prec1', 'prec5')},
+            'training_steps': tr.training_steps, 'lr': opt.get_lr()[0]}
+    post_stats = tensor_stats(model.state_dict())
+
+    # ---- 4. resnet50 summary at a small size: 2 warm steps then a recorded step ----
+    torch.manual_seed(123)
+    model = ref_models.resnet(dataset='imagenet', depth=50)
+    x50, y50 = synth(4, (3, 64, 64), 1000)
+    opt = ref_optim.OptimRegime(model, model.regime)
+    tr = ref_trainer.Trainer(model, ref_ce.CrossEntropyLoss(smooth_eps=0.1), opt, device_ids=None, device='cpu',
+                             dtype=torch.float, print_freq=1000)
+    model.train()
+    l50 = []
+    for _ in range(3):
+        _, loss, _ = tr._step(x50, y50, training=True)
+        l50.append(float(loss))
+    opt.zero_grad()
+    out = model(x50); loss = tr.criterion(out, y50); loss.backward()
+    gn = {n: float(p.grad.norm()) for n, p in model.named_parameters()}
+    np.savez(os.path.join(OUT, 'resnet50_summary.npz'), x=x50.numpy(), y=y50.numpy(), logits=out.detach().numpy(),
+             loss=np.float64(float(loss)), warm_losses=np.array(l50),
+             grad_names=np.array(list(gn.keys())), grad_norms=np.array(list(gn.values())))
+
+    # ---- 5. regimes: LR schedule, Mix&Match size table, sampled order ----
+    reg = {}
+    torch.manual_seed(123)
+    m = ref_models.resnet(dataset='imagenet', depth=50, scale_lr=8, base_devices=8, base_device_batch=256)
+    opt = ref_optim.OptimRegime(m, m.regime, log=False)
+    sched = []
+    for epoch, step in [(0, 0), (0, 1), (0, 300), (0, 1500), (2, 1251), (4, 3000), (5, 3200), (29, 18000),
+                        (30, 18800), (60, 37600), (80, 50100), (89, 55000)]:
+        opt.update(epoch, step)
+        sched.append([epoch, step, opt.get_lr()[0]])
+    reg['resnet50_scale8_lr'] = sched
+    for mode in ('D+', 'B+'):
+        torch.manual_seed(123)
+        m = ref_models.resnet(dataset='imagenet', depth=50, regime='sampled', mix_size_regime=mode,
+                              base_device_batch=256)
+        reg['sampled_' + mode] = [[p, c] for p, c in m.sampled_data_regime]
+        reg['sampled_regularizers'] = [r['name'] for r in m.regime[0]['regularizer']]
+    torch.manual_seed(123)
+    m = ref_models.resnet(dataset='cifar10', depth=20)
+    opt = ref_optim.OptimRegime(m, m.regime, log=False)
+    cif = []
+    for epoch in (0, 80, 81, 121, 122, 164, 170):
+        opt.update(epoch, epoch * 100)
+        cif.append([epoch, opt.get_lr()[0]])
+    reg['resnet20_lr'] = cif
+    wd_names = [n for n, _ in opt.regularizer.regularization_list[0]._named_parameters]
+    reg['resnet20_wd_params'] = wd_names
+    with open(os.path.join(OUT, 'loop_and_regimes.json'), 'w') as f:
+        json.dump({'loop': loop, 'loop_post_stats': post_stats, 'regimes': reg}, f)
+    print('golden written to', OUT)
+
+
+if __name__ == '__main__':
+    main()

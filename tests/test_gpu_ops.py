@@ -1,0 +1,270 @@
+"""Op-level parity of the HBM-bound kernels (BN, pooling, layout transforms, loss, optimizer, depthwise
+conv) against fp64/fp32 torch references on bf16-rounded operands.  Tolerances: SURVEY.md section 8c
+(bf16 outputs: <= 2^-7 of the tensor max; fp32 outputs: rel-L2 <= 1e-5 * sqrt(reduction/1e4))."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def _ops():
+    from convnet.pytorch_b200 import ops
+    return ops
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def close_bf16(a, ref, tol=2 ** -7):
+    a, ref = a.double(), ref.double()
+    return float((a - ref).abs().max()) <= tol * float(ref.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("M,C", [(128, 64), (1000, 16), (6272, 256), (333, 24), (50, 2048), (25088, 64)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_bn_forward_backward(M, C, act):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + C + act)
+    z = (torch.randn(M, C, generator=g) * 1.5 + 0.3).cuda().to(bf16)
+    gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+    beta = (torch.randn(C, generator=g) * 0.2).cuda()
+    rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    nbt = torch.zeros((), dtype=torch.int64).cuda()
+    mean, invstd, scale, shift = [torch.empty(C).cuda() for _ in range(4)]
+    ws = torch.empty(ops.bn_workspace_floats(C)).cuda()
+    res = torch.randn(M, C, generator=g).cuda().to(bf16)
+    ops.bn_stats(z, gamma, beta, 1e-5, 0.1, rm, rv, nbt, mean, invstd, scale, shift, ws)
+    y = ops.bn_apply(z, scale, shift, act, residual=res)
+    torch.cuda.synchronize()
+    # reference
+    zd = z.double().requires_grad_(True)
+    mu = zd.mean(0)
+    var = zd.var(0, unbiased=False)
+    xhat = (zd - mu) / torch.sqrt(var + 1e-5)
+    pre = xhat * gamma.double() + beta.double() + res.double()
+    yref = pre.relu() if act == 1 else (pre.clamp(0, 6) if act == 2 else pre)
+    assert rel(mean, mu.detach()) < 1e-5 and rel(invstd, 1 / torch.sqrt(var.detach() + 1e-5)) < 1e-5
+    assert rel(rm, 0.1 * mu.detach()) < 1e-5
+    assert rel(rv, 0.9 + 0.1 * zd.detach().var(0, unbiased=True)) < 1e-5
+    assert int(nbt) == 1
+    assert close_bf16(y, yref.detach())
+    # backward: use the kernel's own (bf16) y for the activation mask, as the engine does
+    dy = torch.randn(M, C, generator=g).cuda().to(bf16)
+    yk = y.double()
+    mask = torch.ones_like(yk) if act == 0 else ((yk > 0).double() if act == 1 else ((yk > 0) & (yk < 6)).double())
+    gd = dy.double() * mask
+    sums = torch.empty(2 * C).cuda()
+    dgam, dbet = torch.zeros(C).cuda(), torch.zeros(C).cuda()
+    ops.bn_bwd_reduce(dy, y, z, act, mean, invstd, sums, dgam, dbet, ws)
+    gout = torch.empty_like(dy)
+    dz = ops.bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, sums, g_out=gout)
+    torch.cuda.synchronize()
+    (pre_lin := xhat * gamma.double() + beta.double())
+    dzd, dgam_ref, dbet_ref = torch.autograd.grad(pre_lin, [zd, ], gd, retain_graph=True)[0], \
+        (gd * xhat.detach()).sum(0), gd.sum(0)
+    tol = 1e-5 * math.sqrt(max(M, 1e4) / 1e4) * 10
+    assert rel(dgam, dgam_ref) < tol and rel(dbet, dbet_ref) < tol
+    assert rel(sums[:C], dgam_ref) < tol
+    assert close_bf16(dz, dzd)
+    assert close_bf16(gout, gd)
+    # accumulate semantics of dgamma/dbeta
+    ops.bn_bwd_reduce(dy, y, z, act, mean, invstd, sums, dgam, dbet, ws)
+    torch.cuda.synchronize()
+    assert rel(dgam, 2 * dgam_ref) < tol
+
+
+def test_bn_dual_apply_and_eval():
+    ops = _ops()
+    M, C = 777, 128
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(M, C, generator=g).cuda().to(bf16)
+    z2 = torch.randn(M, C, generator=g).cuda().to(bf16)
+    s1, b1, s2, b2 = [torch.randn(C, generator=g).cuda() for _ in range(4)]
+    y = ops.bn_apply(z, s1, b1, 1, z2=z2, scale2=s2, shift2=b2)
+    ref = (z.double() * s1.double() + b1.double() + z2.double() * s2.double() + b2.double()).relu()
+    assert close_bf16(y, ref)
+    gamma, beta = torch.rand(C).cuda() + 0.5, torch.randn(C).cuda()
+    rm, rv = torch.randn(C).cuda(), torch.rand(C).cuda() + 0.5
+    sc, sh = torch.empty(C).cuda(), torch.empty(C).cuda()
+    ops.bn_eval_coeffs(gamma, beta, rm, rv, 1e-5, sc, sh)
+    y = ops.bn_apply(z, sc, sh, 0)
+    ref = F.batch_norm(z.double(), rm.double(), rv.double(), gamma.double(), beta.double(), False, 0.1, 1e-5)
+    assert close_bf16(y, ref)
+
+
+def test_bn_cumulative_momentum():
+    ops = _ops()
+    C = 32
+    rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    nbt = torch.zeros((), dtype=torch.int64).cuda()
+    ws = torch.empty(ops.bn_workspace_floats(C)).cuda()
+    bn = torch.nn.BatchNorm2d(C, momentum=None).double()
+    bufs = [torch.empty(C).cuda() for _ in range(4)]
+    for i in range(3):
+        z = torch.randn(4, 5, 5, C).cuda().to(bf16)
+        ops.bn_stats(z, None, None, 1e-5, None, rm, rv, nbt, *bufs, ws)
+        bn(z.double().cpu().permute(0, 3, 1, 2))
+    assert int(nbt) == 3
+    assert rel(rm.cpu(), bn.running_mean) < 1e-5 and rel(rv.cpu(), bn.running_var) < 1e-5
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 112, 112, 64), (3, 17, 23, 16), (1, 8, 8, 8)])
+def test_maxpool(N, H, W, C):
+    ops = _ops()
+    x = torch.randn(N, H, W, C).cuda().to(bf16)
+    y, am = ops.maxpool_fwd(x)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    assert torch.equal(y.permute(0, 3, 1, 2).float(), yr)
+    dy = torch.randn_like(y)
+    dx = ops.maxpool_bwd(dy, am, (N, H, W, C))
+    dxr, = torch.autograd.grad(yr, xr, dy.float().permute(0, 3, 1, 2))
+    assert close_bf16(dx.permute(0, 3, 1, 2), dxr, 2 ** -7)
+
+
+def test_avgpool():
+    ops = _ops()
+    x = torch.randn(5, 7, 7, 256).cuda().to(bf16)
+    y = ops.avgpool_fwd(x)
+    assert close_bf16(y.view(5, 256), x.double().mean((1, 2)))
+    dy = torch.randn(5, 1, 1, 256).cuda().to(bf16)
+    dx = ops.avgpool_bwd(dy, (5, 7, 7, 256))
+    assert close_bf16(dx, (dy.double() / 49).expand(5, 7, 7, 256))
+
+
+def test_input_prep_and_stem_weights():
+    ops = _ops()
+    x = torch.randn(3, 3, 32, 48).cuda()
+    o = ops.input_prep(x, 16)
+    ref = torch.zeros(3, 32, 48, 16, device='cuda')
+    ref[..., :3] = x.permute(0, 2, 3, 1)
+    assert torch.equal(o.float(), ref.to(bf16).float())
+    o = ops.input_prep(x, 16, s2d=True)
+    ref = torch.zeros(3, 16, 24, 16, device='cuda')
+    for dy in range(2):
+        for dx in range(2):
+            ref[..., (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = x[:, :, dy::2, dx::2].permute(0, 2, 3, 1)
+    assert torch.equal(o.float(), ref.to(bf16).float())
+    # s2d stem == 7x7/s2/p3 conv
+    w = torch.randn(8, 7, 7, 3).cuda()      # KRSC
+    ws = torch.empty(8, 16, 16, device='cuda', dtype=bf16)
+    ops.stem_weight_to_s2d(w, 8, 3, 16, ws)
+    xs = ops.input_prep(x, 16, s2d=True)
+    desc = ops.make_desc(3, 16, 24, 16, 8, 4, 4, 1, 2, P=16, Q=24)
+    y = ops.conv_fprop(xs, ws, desc)
+    yref = F.conv2d(x.to(bf16).double(), w.to(bf16).double().permute(0, 3, 1, 2), stride=2, padding=3)
+    assert close_bf16(y.permute(0, 3, 1, 2), yref)
+    dws = torch.randn(8, 16, 16).cuda()
+    dw = torch.zeros(8, 7, 7, 3).cuda()
+    ops.stem_wgrad_from_s2d(dws, 8, 3, 16, dw)
+    # adjoint check: <to_s2d(w), dws> == <w, from_s2d(dws)> (bf16 rounding of w avoided by using exact values)
+    wq = w.to(bf16).float()
+    ops.stem_weight_to_s2d(wq, 8, 3, 16, ws)
+    assert abs(float((ws.float() * dws).sum()) - float((wq * dw).sum())) < 1e-2
+
+
+def test_weight_transpose_and_cast():
+    ops = _ops()
+    w = torch.randn(70, 9, 40).cuda().to(bf16)
+    assert torch.equal(ops.weight_transpose(w), w.permute(2, 1, 0).contiguous())
+    src = torch.randn(100003).cuda()
+    dst = torch.empty(100003, device='cuda', dtype=bf16)
+    ops.cast_bf16(src, dst)
+    assert torch.equal(dst, src.to(bf16))
+
+
+@pytest.mark.parametrize("B,K,ld,eps", [(64, 1000, 1000, 0.0), (37, 10, 16, 0.0), (64, 1000, 1000, 0.1)])
+def test_softmax_ce(B, K, ld, eps):
+    ops = _ops()
+    from convnet.pytorch_b200.utils.cross_entropy import cross_entropy
+    logits = torch.zeros(B, ld).cuda()
+    logits[:, :K] = torch.randn(B, K).cuda() * 3
+    target = torch.randint(0, K, (B,)).cuda()
+    loss = torch.zeros(1).cuda()
+    dl = torch.empty(B, ld, device='cuda', dtype=bf16)
+    ops.softmax_ce(logits, target, K, eps, 2.0, loss, dl)
+    lr = logits[:, :K].double().requires_grad_(True)
+    ref = cross_entropy(lr, target, smooth_eps=eps if eps else None)
+    gref, = torch.autograd.grad(ref, lr)
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert close_bf16(dl[:, :K], 2.0 * gref)
+    assert float(dl[:, K:].float().abs().sum()) == 0.0
+
+
+def test_colsum():
+    ops = _ops()
+    m = torch.randn(256, 1000).cuda().to(bf16)
+    out = torch.ones(1000).cuda()
+    ops.colsum_bf16(m, out)
+    assert rel(out, 1 + m.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("n,wd_count", [(1000003, 700000), (4096, 4096), (17, 0)])
+def test_fused_sgd_matches_reference_chain(n, wd_count):
+    """unscale -> WeightDecay.pre_step -> torch.optim.SGD(momentum) -> bf16 copy, three steps."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g).cuda()
+    p = p0.clone()
+    m = torch.zeros(n).cuda()
+    p16 = torch.empty(n, device='cuda', dtype=bf16)
+    pref = p0.clone().double().requires_grad_(True)
+    opt = torch.optim.SGD([pref], lr=0.1, momentum=0.9)
+    for step in range(3):
+        grad = torch.randn(n, generator=g).cuda() * 128.0
+        ops.fused_sgd(p, grad, m, p16, n, wd_count, 0.1, 0.9, 0.0, 1e-4, 1.0 / 128.0, None, step == 0)
+        gr = grad.double() / 128.0
+        gr[:wd_count] += 1e-4 * pref.detach()[:wd_count]
+        pref.grad = gr
+        opt.step()
+    torch.cuda.synchronize()
+    assert rel(p, pref.detach()) < 1e-6
+    assert rel(m, opt.state[pref]['momentum_buffer']) < 1e-6
+    assert torch.equal(p16, p.to(bf16))
+
+
+def test_sumsq_and_grad_coef():
+    ops = _ops()
+    g = torch.randn(3000001).cuda() * 64
+    out = torch.zeros(8).cuda()
+    ws = torch.empty(1024).cuda()
+    ops.sumsq(g, g.numel(), out[0:1], ws)
+    assert rel(out[0], (g.double() ** 2).sum()) < 1e-6
+    norm = float(g.double().norm()) / 64
+    ops.grad_coef(out[0:1], 1 / 64., 0, 5.0, 0.0, None, out[1:2], out[2:3])
+    assert abs(float(out[2]) - norm) / norm < 1e-5 and abs(float(out[1]) - min(1.0, 5.0 / (norm + 1e-6))) < 1e-6
+    state = out[4:6]
+    ops.grad_coef(out[0:1], 1 / 64., 1, 0.0, 0.9, state, out[1:2], out[2:3])
+    assert float(out[1]) == 1.0 and abs(float(state[0]) - norm) / norm < 1e-5
+    g2 = g * 2
+    ops.sumsq(g2, g2.numel(), out[0:1], ws)
+    ops.grad_coef(out[0:1], 1 / 64., 1, 0.0, 0.9, state, out[1:2], out[2:3])
+    run = 0.9 * norm + 0.1 * 2 * norm
+    assert abs(float(out[1]) - run / (2 * norm + 1e-6)) < 1e-5
+
+
+@pytest.mark.parametrize("N,H,C,stride", [(2, 28, 96, 1), (2, 56, 144, 2), (1, 7, 960, 1), (3, 14, 24, 2)])
+def test_depthwise(N, H, C, stride):
+    ops = _ops()
+    x = torch.randn(N, H, H, C).cuda().to(bf16)
+    w = (torch.randn(9, C) / 3).cuda().to(bf16)
+    desc = ops.make_desc(N, H, H, C, C, 3, 3, stride, 1)
+    y = ops.dwconv_fprop(x, w, desc)
+    xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.double().t().reshape(C, 1, 3, 3).requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=stride, padding=1, groups=C)
+    assert close_bf16(y.permute(0, 3, 1, 2), yr.detach())
+    dy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(yr, [xr, wr], dy.double().permute(0, 3, 1, 2))
+    dx = ops.dwconv_dgrad(dy, w, desc)
+    assert close_bf16(dx.permute(0, 3, 1, 2), gx)
+    dw = torch.zeros(9, C).cuda()
+    ws = torch.empty(592 * 9 * C).cuda()
+    ops.dwconv_wgrad(x, dy, desc, dw, ws)
+    assert rel(dw, gw.reshape(C, 9).t()) < 1e-5
