@@ -89,12 +89,24 @@ class ClockSampler(threading.Thread):
                 'power_w_max': max(float(s[2]) for s in self.samples), 'samples': len(self.samples)}
 
 
+def usable_cores():
+    """host threads this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference(batch, steps, warmup, depth):
     """The reference's CPU trainer path (oracle port of models/resnet.py + Trainer._step + OptimRegime.step),
     fp32, all host threads, on a bounded sample of the workload (batch ``batch`` instead of 256)."""
     from oracle import ref_model
     from convnet.pytorch_b200 import models
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(int(os.environ.get('B200_CPU_THREADS', usable_cores())))
     torch.manual_seed(123)
     sd = {k: v.clone() for k, v in models.resnet(dataset='imagenet', depth=depth).state_dict().items()}
     g = torch.Generator().manual_seed(0)

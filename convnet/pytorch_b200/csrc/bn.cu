@@ -1,35 +1,49 @@
 // Batch-norm statistics / apply / backward for NHWC bf16 activations: HBM-bound, 128-bit vectorised,
-// deterministic two-level reductions (per-block partials -> finalize), ReLU/ReLU6 and the residual add
-// fused.  Replaces nn.BatchNorm2d (+ nn.ReLU, + `out += residual`) of the reference
-// (models/resnet.py:88-91,115-116,128-134,162-163; models/mobilenet_v2.py:50-63) in train and eval.
+// ReLU/ReLU6 and the residual add fused.  Replaces nn.BatchNorm2d (+ nn.ReLU, + `out += residual`) of the
+// reference (models/resnet.py:88-91,115-116,128-134,162-163; models/mobilenet_v2.py:50-63), train and eval.
 //
 // Thread mapping shared by all kernels: a block owns a contiguous range of rows (pixels); thread t is
-// (row_in_iter = t / cv, vec = t % cv) with cv = C/8 channel vectors, so every iteration of a block
-// touches one contiguous span of memory and per-channel coefficients are loaded once per thread.
+// (row_in_iter = t / cv, vec = t % cv) with cv = C/8 channel vectors, so every iteration of a block touches
+// one contiguous span of memory and per-channel coefficients are loaded once per thread.
+//
+// Reductions are single-kernel: per-block partial sums (registers -> shared) are added into fp64 accumulators
+// in the workspace with atomicAdd(double); the last block to finish (ticket counter) finalises and re-zeroes
+// the workspace.  The workspace must be zero before first use and must not be shared by concurrent streams.
 #include "common.cuh"
 #include "host.h"
 
 namespace b200 {
 
 constexpr int kBnThreads = 256;
+constexpr int kBnMaxC = 2048;
 constexpr int kBnMaxBlocks = 1184;  // 8 per SM on 148 SMs
+constexpr int kWsFloats = 2 * kBnMaxC * 2 + 64;  // 2*C doubles + ticket counter
 
 struct RowMap {
-  int cv, rows_per_iter, active;
+  int cv, rows_per_iter;
 };
 static inline RowMap make_rowmap(int C) {
   RowMap m;
   m.cv = C / 8;
   m.rows_per_iter = kBnThreads / m.cv;
-  m.active = m.rows_per_iter * m.cv;
   return m;
 }
-static inline int bn_blocks(long long M, const RowMap& rm) {
+static inline int reduce_blocks(long long M, int C, const RowMap& rm) {
   long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
-  long long want = (iters + 3) / 4;  // >= 4 iterations per block
+  long long want = (iters + 7) / 8;          // >= 8 row-iterations per block
+  long long cap = 400000LL / (2 * C);        // bound the number of fp64 atomics (blocks * 2C)
+  if (cap < sm_count()) cap = sm_count();
+  if (cap > kBnMaxBlocks) cap = kBnMaxBlocks;
+  if (want > cap) want = cap;
   if (want < 1) want = 1;
-  if (want > kBnMaxBlocks) want = kBnMaxBlocks;
   return (int)want;
+}
+static inline int stream_blocks(long long M, const RowMap& rm) {
+  long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
+  long long blocks = (iters + 7) / 8;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 4 * kBnMaxBlocks) blocks = 4 * kBnMaxBlocks;
+  return (int)blocks;
 }
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
@@ -48,17 +62,18 @@ __device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
-__device__ __forceinline__ float act_mask(float y, int act) {
-  if (act == B200_ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (act == B200_ACT_RELU6) return (y > 0.f && y < 6.f) ? 1.f : 0.f;
+__device__ __forceinline__ float act_mask(float v, int act) {
+  if (act == B200_ACT_RELU) return v > 0.f ? 1.f : 0.f;
+  if (act == B200_ACT_RELU6) return (v > 0.f && v < 6.f) ? 1.f : 0.f;
   return 1.f;
 }
 
-// block-level reduction of 16 per-thread values over the rows_per_iter threads sharing a channel vector;
-// writes partial[block][stat(2)][C]
-__device__ __forceinline__ void block_reduce_write(float (&acc)[16], int cv, int rows_per_iter, int C,
-                                                   float* partial_blk) {
+// Block partials -> fp64 global accumulators; returns true in the LAST block of the grid (after a grid-wide
+// happens-before: every other block's atomics are visible).
+__device__ __forceinline__ bool accumulate_and_elect(float (&acc)[16], int cv, int rows_per_iter, int C,
+                                                     double* accum, unsigned* ticket) {
   __shared__ float red[kBnThreads][17];
+  __shared__ bool is_last;
   const int t = threadIdx.x;
 #pragma unroll
   for (int i = 0; i < 16; ++i) red[t][i] = acc[i];
@@ -69,14 +84,22 @@ __device__ __forceinline__ void block_reduce_write(float (&acc)[16], int cv, int
     const int v = c >> 3, e = c & 7;
     float s = 0.f;
     for (int r = 0; r < rows_per_iter; ++r) s += red[r * cv + v][stat * 8 + e];
-    partial_blk[o] = s;
+    atomicAdd(accum + o, (double)s);
   }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
 }
 
 // ---- forward statistics -------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBnThreads) bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ z,
-                                                                      long long M, int C, int cv,
-                                                                      int rows_per_iter, float* __restrict__ partial) {
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(
+    const __nv_bfloat16* __restrict__ z, long long M, int C, int cv, int rows_per_iter,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+    float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
+    double* accum, unsigned* ticket) {
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -104,62 +127,39 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_partial_kernel(const __nv
       for (int i = 0; i < 8; ++i) { acc[i] += f[i]; acc[8 + i] += f[i] * f[i]; }
     }
   }
-  block_reduce_write(acc, cv, rows_per_iter, C, partial + (long long)blockIdx.x * 2 * C);
-}
-
-// second-level reduction: 16 channels x 16 slices of the partial blocks per CTA, doubles across slices
-__device__ __forceinline__ bool reduce_partials16(const float* __restrict__ partial, int nblocks, int C, int& c_out,
-                                                  double& s1_out, double& s2_out) {
-  __shared__ double sh[2][16][17];
-  const int cl = threadIdx.x & 15, sl = threadIdx.x >> 4;
-  const int c = blockIdx.x * 16 + cl;
-  double s1 = 0.0, s2 = 0.0;
-  if (c < C) {
-    for (int b = sl; b < nblocks; b += 16) {
-      s1 += (double)partial[(long long)b * 2 * C + c];
-      s2 += (double)partial[(long long)b * 2 * C + C + c];
+  if (!accumulate_and_elect(acc, cv, rows_per_iter, C, accum, ticket)) return;
+  // ---- last block: finalise ----
+  float f = momentum;
+  if (momentum < 0.f) {  // cumulative moving average (momentum=None): factor 1/(num_batches_tracked+1)
+    const long long nbt = num_batches_tracked ? *num_batches_tracked : 0;
+    f = 1.f / (float)(nbt + 1);
+  }
+  for (int c = t; c < C; c += kBnThreads) {
+    const double s1 = __ldcg(accum + c), s2 = __ldcg(accum + C + c);
+    accum[c] = 0.0;
+    accum[C + c] = 0.0;
+    const double mu = s1 / (double)M;
+    double var = s2 / (double)M - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float istd = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = (float)mu;
+    invstd[c] = istd;
+    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    const float sc = g * istd;
+    scale[c] = sc;
+    shift[c] = bt - (float)mu * sc;
+    if (running_mean != nullptr && running_var != nullptr) {
+      const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_mean[c] = (1.f - f) * running_mean[c] + f * (float)mu;
+      running_var[c] = (1.f - f) * running_var[c] + f * (float)unbiased;
     }
   }
-  sh[0][sl][cl] = s1;
-  sh[1][sl][cl] = s2;
   __syncthreads();
-  if (sl != 0 || c >= C) return false;
-  s1 = 0.0; s2 = 0.0;
-  for (int i = 0; i < 16; ++i) { s1 += sh[0][i][cl]; s2 += sh[1][i][cl]; }
-  c_out = c; s1_out = s1; s2_out = s2;
-  return true;
-}
-
-__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ partial, int nblocks,
-                                         long long M, int C,
-                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                         float momentum, float* running_mean, float* running_var,
-                                         long long* num_batches_tracked, float* mean, float* invstd, float* scale,
-                                         float* shift) {
-  int c; double s1, s2;
-  if (!reduce_partials16(partial, nblocks, C, c, s1, s2)) return;
-  const double mu = s1 / (double)M;
-  double var = s2 / (double)M - mu * mu;
-  if (var < 0.0) var = 0.0;
-  const float istd = (float)(1.0 / sqrt(var + (double)eps));
-  mean[c] = (float)mu;
-  invstd[c] = istd;
-  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
-  const float sc = g * istd;
-  scale[c] = sc;
-  shift[c] = bt - (float)mu * sc;
-  if (running_mean != nullptr && running_var != nullptr) {
-    float f = momentum;
-    if (momentum < 0.f) {  // cumulative moving average (momentum=None), factor = 1/(num_batches_tracked+1)
-      const long long nbt = num_batches_tracked ? *num_batches_tracked : 0;
-      f = 1.f / (float)(nbt + 1);
-    }
-    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-    running_mean[c] = (1.f - f) * running_mean[c] + f * (float)mu;
-    running_var[c] = (1.f - f) * running_var[c] + f * (float)unbiased;
+  if (t == 0) {
+    *ticket = 0u;
+    if (num_batches_tracked != nullptr && running_mean != nullptr) *num_batches_tracked += 1;
   }
 }
-__global__ void bn_bump_counter_kernel(long long* num_batches_tracked) { *num_batches_tracked += 1; }
 
 __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv,
                                       float eps, float* scale, float* shift) {
@@ -173,14 +173,10 @@ __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* be
 
 // ---- forward apply ------------------------------------------------------------------------------
 template <int MODE>  // 0: none, 1: + residual, 2: + (z2*scale2+shift2)
-__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long M, int C,
-                                                              int cv, int rows_per_iter,
-                                                              const float* __restrict__ scale,
-                                                              const float* __restrict__ shift,
-                                                              const __nv_bfloat16* __restrict__ res,
-                                                              const float* __restrict__ scale2,
-                                                              const float* __restrict__ shift2, int act,
-                                                              __nv_bfloat16* __restrict__ y) {
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
+    const __nv_bfloat16* __restrict__ z, long long M, int C, int cv, int rows_per_iter,
+    const float* __restrict__ scale, const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
+    const float* __restrict__ scale2, const float* __restrict__ shift2, int act, __nv_bfloat16* __restrict__ y) {
   const int t = threadIdx.x;
   if (t >= rows_per_iter * cv) return;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -204,9 +200,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const __nv_bfloat1
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float a = fa[i] * sc[i] + sh[i];
-      float b = fb[i] * sc[i] + sh[i];
-      if (MODE == 1) { a += ga[i]; b += gb[i]; }
-      if (MODE == 2) { a += ga[i] * sc2[i] + sh2[i]; b += gb[i] * sc2[i] + sh2[i]; }
+      float b = hb ? fb[i] * sc[i] + sh[i] : 0.f;
+      if (MODE == 1) { a += ga[i]; if (hb) b += gb[i]; }
+      if (MODE == 2) { a += ga[i] * sc2[i] + sh2[i]; if (hb) b += gb[i] * sc2[i] + sh2[i]; }
       if (act == B200_ACT_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
       if (act == B200_ACT_RELU6) { a = fminf(fmaxf(a, 0.f), 6.f); b = fminf(fmaxf(b, 0.f), 6.f); }
       fa[i] = a; fb[i] = b;
@@ -216,91 +212,109 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const __nv_bfloat1
   }
 }
 
-// ---- backward reduce: dbeta = sum g, dgamma = sum g * xhat, g = dy * act'(y) ---------------------
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                                    const __nv_bfloat16* __restrict__ y,
-                                                                    const __nv_bfloat16* __restrict__ z, long long M,
-                                                                    int C, int cv, int rows_per_iter, int act,
-                                                                    const float* __restrict__ mean,
-                                                                    const float* __restrict__ invstd,
-                                                                    float* __restrict__ partial) {
+// g = dy * act'(.), where the activation argument is y when given, else recomputed as z*scale+shift
+struct MaskSrc {
+  float sc[8], sh[8];
+};
+__device__ __forceinline__ void masked_grad(const float (&dy)[8], const float (&z)[8], const float (&y)[8],
+                                            bool have_y, int act, const MaskSrc& ms, float (&g)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float gi = dy[i];
+    if (act != B200_ACT_NONE) gi *= act_mask(have_y ? y[i] : fmaf(z[i], ms.sc[i], ms.sh[i]), act);
+    g[i] = gi;
+  }
+}
+
+// ---- backward reduce: dbeta = sum g, dgamma = sum g * xhat ------------------------------------------
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
+    long long M, int C, int cv, int rows_per_iter, int act, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, float* sums,
+    float* dgamma_acc, float* dbeta_acc, double* accum, unsigned* ticket) {
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
   const int r0 = t / cv, v = t - r0 * cv;
   const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
   const long long row_begin = blockIdx.x * rows_per_block;
   const long long row_end = min(M, row_begin + rows_per_block);
+  const bool have_y = (y != nullptr);
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   if (active) {
     float mu[8], is[8];
+    MaskSrc ms;
     loadf8(mean + v * 8, mu);
     loadf8(invstd + v * 8, is);
+    if (act != B200_ACT_NONE && !have_y) {
+      float ga[8], be[8];
+      if (gamma) loadf8(gamma + v * 8, ga);
+      if (beta) loadf8(beta + v * 8, be);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ms.sc[i] = (gamma ? ga[i] : 1.f) * is[i];
+        ms.sh[i] = (beta ? be[i] : 0.f) - mu[i] * ms.sc[i];
+      }
+    }
     for (long long r = row_begin + r0; r < row_end; r += 2LL * rows_per_iter) {
       const long long rb = r + rows_per_iter;
       const bool hb = rb < row_end;
-      float da[8], db[8], za[8], zb[8], ya[8], yb[8];
+      float da[8], db[8], za[8], zb[8], ya[8], yb[8], ga[8], gb[8];
       load8(dy + r * C + v * 8, da);
       load8(z + r * C + v * 8, za);
-      if (act != B200_ACT_NONE) load8(y + r * C + v * 8, ya);
+      if (have_y && act != B200_ACT_NONE) load8(y + r * C + v * 8, ya);
       if (hb) {
         load8(dy + rb * C + v * 8, db);
         load8(z + rb * C + v * 8, zb);
-        if (act != B200_ACT_NONE) load8(y + rb * C + v * 8, yb);
+        if (have_y && act != B200_ACT_NONE) load8(y + rb * C + v * 8, yb);
       }
+      masked_grad(da, za, ya, have_y, act, ms, ga);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float g = da[i];
-        if (act != B200_ACT_NONE) g *= act_mask(ya[i], act);
-        acc[i] += g * (za[i] - mu[i]) * is[i];
-        acc[8 + i] += g;
-        if (hb) {
-          float g2 = db[i];
-          if (act != B200_ACT_NONE) g2 *= act_mask(yb[i], act);
-          acc[i] += g2 * (zb[i] - mu[i]) * is[i];
-          acc[8 + i] += g2;
-        }
+      for (int i = 0; i < 8; ++i) { acc[i] += ga[i] * (za[i] - mu[i]) * is[i]; acc[8 + i] += ga[i]; }
+      if (hb) {
+        masked_grad(db, zb, yb, have_y, act, ms, gb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] += gb[i] * (zb[i] - mu[i]) * is[i]; acc[8 + i] += gb[i]; }
       }
     }
   }
-  block_reduce_write(acc, cv, rows_per_iter, C, partial + (long long)blockIdx.x * 2 * C);
-}
-
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
-                                       float* sums, float* dgamma_acc, float* dbeta_acc) {
-  int c; double s1, s2;
-  if (!reduce_partials16(partial, nblocks, C, c, s1, s2)) return;
-  sums[c] = (float)s1;
-  sums[C + c] = (float)s2;
-  if (dgamma_acc) dgamma_acc[c] += (float)s1;
-  if (dbeta_acc) dbeta_acc[c] += (float)s2;
+  if (!accumulate_and_elect(acc, cv, rows_per_iter, C, accum, ticket)) return;
+  for (int c = t; c < C; c += kBnThreads) {
+    const float s1 = (float)__ldcg(accum + c), s2 = (float)__ldcg(accum + C + c);
+    accum[c] = 0.0;
+    accum[C + c] = 0.0;
+    sums[c] = s1;
+    sums[C + c] = s2;
+    if (dgamma_acc) dgamma_acc[c] += s1;
+    if (dbeta_acc) dbeta_acc[c] += s2;
+  }
+  __syncthreads();
+  if (t == 0) *ticket = 0u;
 }
 
 // ---- backward dx --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                               const __nv_bfloat16* __restrict__ y,
-                                                               const __nv_bfloat16* __restrict__ z, long long M, int C,
-                                                               int cv, int rows_per_iter, int act,
-                                                               const float* __restrict__ mean,
-                                                               const float* __restrict__ invstd,
-                                                               const float* __restrict__ gamma,
-                                                               const float* __restrict__ sums,
-                                                               __nv_bfloat16* __restrict__ dz,
-                                                               __nv_bfloat16* __restrict__ g_out) {
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_dx_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
+    long long M, int C, int cv, int rows_per_iter, int act, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out) {
   const int t = threadIdx.x;
   if (t >= rows_per_iter * cv) return;
   const int r0 = t / cv, v = t - r0 * cv;
   const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
   const long long row_begin = blockIdx.x * rows_per_block;
   const long long row_end = min(M, row_begin + rows_per_block);
+  const bool have_y = (y != nullptr);
   // dz = A*g + B*z + Cc  with A = gamma*istd, B = -gamma*istd^2*dgamma/M, Cc = -A*dbeta/M - B*mean
   float A[8], B[8], Cc[8];
+  MaskSrc ms;
   {
-    float mu[8], is[8], ga[8], dg[8], dbt[8];
+    float mu[8], is[8], ga[8], be[8], dg[8], dbt[8];
     loadf8(mean + v * 8, mu);
     loadf8(invstd + v * 8, is);
     if (gamma) loadf8(gamma + v * 8, ga);
+    if (beta) loadf8(beta + v * 8, be);
     loadf8(sums + v * 8, dg);
     loadf8(sums + C + v * 8, dbt);
     const float invM = 1.f / (float)M;
@@ -310,53 +324,50 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_dx_kernel(const __nv_bfloat
       A[i] = gm * is[i];
       B[i] = -gm * is[i] * is[i] * dg[i] * invM;
       Cc[i] = -A[i] * dbt[i] * invM - B[i] * mu[i];
+      ms.sc[i] = A[i];
+      ms.sh[i] = (beta ? be[i] : 0.f) - mu[i] * A[i];
     }
   }
   for (long long r = row_begin + r0; r < row_end; r += 2LL * rows_per_iter) {
     const long long rb = r + rows_per_iter;
     const bool hb = rb < row_end;
-    float da[8], db[8], za[8], zb[8], ya[8], yb[8];
+    float da[8], db[8], za[8], zb[8], ya[8], yb[8], ga[8], gb[8];
     load8(dy + r * C + v * 8, da);
     load8(z + r * C + v * 8, za);
-    if (act != B200_ACT_NONE) load8(y + r * C + v * 8, ya);
+    if (have_y && act != B200_ACT_NONE) load8(y + r * C + v * 8, ya);
     if (hb) {
       load8(dy + rb * C + v * 8, db);
       load8(z + rb * C + v * 8, zb);
-      if (act != B200_ACT_NONE) load8(y + rb * C + v * 8, yb);
+      if (have_y && act != B200_ACT_NONE) load8(y + rb * C + v * 8, yb);
     }
+    masked_grad(da, za, ya, have_y, act, ms, ga);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float g = da[i];
-      if (act != B200_ACT_NONE) g *= act_mask(ya[i], act);
-      da[i] = g;
-      za[i] = A[i] * g + B[i] * za[i] + Cc[i];
-      if (hb) {
-        float g2 = db[i];
-        if (act != B200_ACT_NONE) g2 *= act_mask(yb[i], act);
-        db[i] = g2;
-        zb[i] = A[i] * g2 + B[i] * zb[i] + Cc[i];
-      }
-    }
+    for (int i = 0; i < 8; ++i) za[i] = A[i] * ga[i] + B[i] * za[i] + Cc[i];
     store8(dz + r * C + v * 8, za);
-    if (g_out) store8(g_out + r * C + v * 8, da);
+    if (g_out) store8(g_out + r * C + v * 8, ga);
     if (hb) {
+      masked_grad(db, zb, yb, have_y, act, ms, gb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) zb[i] = A[i] * gb[i] + B[i] * zb[i] + Cc[i];
       store8(dz + rb * C + v * 8, zb);
-      if (g_out) store8(g_out + rb * C + v * 8, db);
+      if (g_out) store8(g_out + rb * C + v * 8, gb);
     }
   }
 }
 
 static int check_c(int C, const char* who) {
-  B200_REQUIRE(C > 0 && C % 8 == 0 && C <= 2048, B200_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 8 and <= 2048",
-               who, C);
+  B200_REQUIRE(C > 0 && C % 8 == 0 && C <= kBnMaxC, B200_ERR_UNSUPPORTED,
+               "%s: C=%d must be a multiple of 8 and <= %d", who, C, kBnMaxC);
   return B200_OK;
 }
+static inline double* ws_accum(float* ws) { return reinterpret_cast<double*>(ws); }
+static inline unsigned* ws_ticket(float* ws) { return reinterpret_cast<unsigned*>(ws + 2 * kBnMaxC * 2); }
 
 }  // namespace b200
 
 using namespace b200;
 
-extern "C" size_t b200_bn_workspace_floats(int C) { return (size_t)kBnMaxBlocks * 2 * (size_t)(C > 0 ? C : 0); }
+extern "C" size_t b200_bn_workspace_floats(int C) { (void)C; return (size_t)kWsFloats; }
 
 extern "C" int b200_bn_stats(const void* z, long long M, int C, const float* gamma, const float* beta, float eps,
                              float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
@@ -364,20 +375,12 @@ extern "C" int b200_bn_stats(const void* z, long long M, int C, const float* gam
   int rc = check_c(C, "bn_stats");
   if (rc) return rc;
   B200_REQUIRE(z && mean && invstd && scale && shift && workspace && M > 0, B200_ERR_INVALID, "bn_stats: bad argument");
-  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, B200_ERR_INVALID, "bn_stats: workspace misaligned");
   const RowMap rm = make_rowmap(C);
-  const int blocks = bn_blocks(M, rm);
-  bn_stats_partial_kernel<<<blocks, kBnThreads, 0, stream>>>((const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter,
-                                                            workspace);
-  B200_CHECK_LAUNCH("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<(C + 15) / 16, 256, 0, stream>>>(workspace, blocks, M, C, gamma, beta, eps, momentum,
-                                                               running_mean, running_var, nbt, mean, invstd, scale,
-                                                               shift);
-  B200_CHECK_LAUNCH("bn_stats_finalize_kernel");
-  if (nbt != nullptr && running_mean != nullptr) {
-    bn_bump_counter_kernel<<<1, 1, 0, stream>>>(nbt);
-    B200_CHECK_LAUNCH("bn_bump_counter_kernel");
-  }
+  bn_stats_kernel<<<reduce_blocks(M, C, rm), kBnThreads, 0, (cudaStream_t)stream_>>>(
+      (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, gamma, beta, eps, momentum, running_mean, running_var,
+      nbt, mean, invstd, scale, shift, ws_accum(workspace), ws_ticket(workspace));
+  B200_CHECK_LAUNCH("bn_stats_kernel");
   return B200_OK;
 }
 
@@ -401,59 +404,47 @@ extern "C" int b200_bn_apply(const void* z, long long M, int C, const float* sca
   B200_REQUIRE(!z2 || (scale2 && shift2), B200_ERR_INVALID, "bn_apply: z2 needs scale2/shift2");
   cudaStream_t stream = (cudaStream_t)stream_;
   const RowMap rm = make_rowmap(C);
-  long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
-  long long blocks = (iters + 7) / 8;
-  if (blocks < 1) blocks = 1;
-  if (blocks > 4 * kBnMaxBlocks) blocks = 4 * kBnMaxBlocks;
+  const int blocks = stream_blocks(M, rm);
   const __nv_bfloat16* zz = (const __nv_bfloat16*)z;
   __nv_bfloat16* yy = (__nv_bfloat16*)y;
   if (residual)
-    bn_apply_kernel<1><<<(int)blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
-                                                               (const __nv_bfloat16*)residual, nullptr, nullptr, act, yy);
+    bn_apply_kernel<1><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
+                                                         (const __nv_bfloat16*)residual, nullptr, nullptr, act, yy);
   else if (z2)
-    bn_apply_kernel<2><<<(int)blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
-                                                               (const __nv_bfloat16*)z2, scale2, shift2, act, yy);
+    bn_apply_kernel<2><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
+                                                         (const __nv_bfloat16*)z2, scale2, shift2, act, yy);
   else
-    bn_apply_kernel<0><<<(int)blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift, nullptr,
-                                                               nullptr, nullptr, act, yy);
+    bn_apply_kernel<0><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift, nullptr,
+                                                         nullptr, nullptr, act, yy);
   B200_CHECK_LAUNCH("bn_apply_kernel");
   return B200_OK;
 }
 
 extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const void* z, long long M, int C, int act,
-                                  const float* mean, const float* invstd, float* sums, float* dgamma_acc,
-                                  float* dbeta_acc, float* workspace, b200_stream_t stream_) {
+                                  const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                  float* sums, float* dgamma_acc, float* dbeta_acc, float* workspace,
+                                  b200_stream_t stream_) {
   int rc = check_c(C, "bn_bwd_reduce");
   if (rc) return rc;
   B200_REQUIRE(dy && z && mean && invstd && sums && workspace && M > 0, B200_ERR_INVALID, "bn_bwd_reduce: bad argument");
-  B200_REQUIRE(act == B200_ACT_NONE || y, B200_ERR_INVALID, "bn_bwd_reduce: activation mask needs y");
-  cudaStream_t stream = (cudaStream_t)stream_;
   const RowMap rm = make_rowmap(C);
-  const int blocks = bn_blocks(M, rm);
-  bn_bwd_partial_kernel<<<blocks, kBnThreads, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
-                                                          (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, act,
-                                                          mean, invstd, workspace);
-  B200_CHECK_LAUNCH("bn_bwd_partial_kernel");
-  bn_bwd_finalize_kernel<<<(C + 15) / 16, 256, 0, stream>>>(workspace, blocks, C, sums, dgamma_acc, dbeta_acc);
-  B200_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  bn_bwd_reduce_kernel<<<reduce_blocks(M, C, rm), kBnThreads, 0, (cudaStream_t)stream_>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, act,
+      mean, invstd, gamma, beta, sums, dgamma_acc, dbeta_acc, ws_accum(workspace), ws_ticket(workspace));
+  B200_CHECK_LAUNCH("bn_bwd_reduce_kernel");
   return B200_OK;
 }
 
 extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const void* z, long long M, int C, int act,
-                              const float* mean, const float* invstd, const float* gamma, const float* sums, void* dz,
-                              void* g_out, b200_stream_t stream_) {
+                              const float* mean, const float* invstd, const float* gamma, const float* beta,
+                              const float* sums, void* dz, void* g_out, b200_stream_t stream_) {
   int rc = check_c(C, "bn_bwd_dx");
   if (rc) return rc;
   B200_REQUIRE(dy && z && mean && invstd && sums && dz && M > 0, B200_ERR_INVALID, "bn_bwd_dx: bad argument");
-  B200_REQUIRE(act == B200_ACT_NONE || y, B200_ERR_INVALID, "bn_bwd_dx: activation mask needs y");
   const RowMap rm = make_rowmap(C);
-  long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
-  long long blocks = (iters + 7) / 8;
-  if (blocks < 1) blocks = 1;
-  if (blocks > 4 * kBnMaxBlocks) blocks = 4 * kBnMaxBlocks;
-  bn_bwd_dx_kernel<<<(int)blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(
+  bn_bwd_dx_kernel<<<stream_blocks(M, rm), kBnThreads, 0, (cudaStream_t)stream_>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, act,
-      mean, invstd, gamma, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);
+      mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);
   B200_CHECK_LAUNCH("bn_bwd_dx_kernel");
   return B200_OK;
 }

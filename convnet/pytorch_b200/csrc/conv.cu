@@ -43,6 +43,7 @@ struct IgemmParams {
   int OH, OW, os, oh0, ow0;
   int ldo;
   int act, out_fp32;
+  int tma_store;         // 1: dense bf16 output staged in smem and written by TMA (tmC), residual via tmR
   void* out;
   const void* res;
   const float* bias;
@@ -118,12 +119,14 @@ __device__ __forceinline__ void store_chunk16(const IgemmParams& p, const uint32
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                   const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ __align__(8) uint64_t res_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
@@ -141,9 +144,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 4);
     mbar_init(&tmem_empty[1], 4);
+    mbar_init(&res_bar, 1);
     fence_mbar_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.tma_store) {
+      prefetch_tmap(&tmC);
+      if (p.res != nullptr) prefetch_tmap(&tmR);
+    }
   }
   if (warp == 1) {
     tmem_alloc(&tmem_base_s, kTmemCols);
@@ -238,10 +246,81 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         off = ((static_cast<long long>(img) * p.OH + (bi * p.os + p.oh0)) * p.OW + (bj * p.os + p.ow0)) *
               static_cast<long long>(p.ldo);
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
       const int nbase = n_tile * p.block_n;
+      if (p.tma_store) {
+        // Dense bf16 output: stage the tile in 128B-swizzled shared memory and write it with TMA (coalesced,
+        // clipped at the M tail); the residual tile is fetched by TMA into the same buffer and updated in place.
+        const bool leader = (warp == 2 && lane == 0);
+        const int row = q * 32 + lane;
+        uint8_t* epi = smem + p.num_stages * stage_bytes;
+        const int nbox = p.block_n >> 6;
+        if (leader && local > 0) bulk_wait_group_read0();  // previous tile's store has finished reading smem
+        named_bar_sync(1, 128);
+        if (p.res != nullptr) {
+          if (leader) {
+            mbar_arrive_expect_tx(&res_bar, static_cast<uint32_t>(nbox) * kTileM * 128u);
+            for (int b = 0; b < nbox; ++b)
+              tma_load_2d(&tmR, &res_bar, epi + b * (kTileM * 128), nbase + b * 64, m_tile * kTileM);
+          }
+          mbar_wait(&res_bar, static_cast<uint32_t>(local & 1));
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + nbase + c0 + i);
+          }
+          uint8_t* box = epi + (c0 >> 6) * (kTileM * 128) + row * 128;
+          const int j0 = (c0 & 63) >> 3;  // 16B chunk index inside the 128B row
+          uint4* p0 = reinterpret_cast<uint4*>(box + (((j0) ^ (row & 7)) << 4));
+          uint4* p1 = reinterpret_cast<uint4*>(box + (((j0 + 1) ^ (row & 7)) << 4));
+          if (p.res != nullptr) {
+            const uint4 r0 = *p0, r1 = *p1;
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 t = unpack_bf16x2(rr[i]);
+              f[2 * i] += t.x;
+              f[2 * i + 1] += t.y;
+            }
+          }
+          if (p.act == B200_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          } else if (p.act == B200_ACT_RELU6) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fminf(fmaxf(f[i], 0.f), 6.f);
+          }
+          uint4 a, b;
+          a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+          a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+          b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+          b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+          *p0 = a;
+          *p1 = b;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // TMEM stage is free: the MMA warp may start tile+2
+        fence_proxy_async();                             // generic-proxy smem writes -> visible to TMA
+        named_bar_sync(1, 128);
+        if (leader) {
+          for (int b = 0; b < nbox; ++b)
+            tma_store_2d(&tmC, epi + b * (kTileM * 128), nbase + b * 64, m_tile * kTileM);
+          bulk_commit_group();
+        }
+        continue;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       int c0 = 0;
       for (; c0 + 32 <= p.block_n; c0 += 32) {
         uint32_t v0[16], v1[16];
@@ -261,6 +340,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (p.tma_store && warp == 2 && lane == 0) bulk_wait_group0();  // smem must outlive the last TMA store
   }
   __syncwarp();
   tc_fence_before();
@@ -290,6 +370,8 @@ struct WgradParams {
   int num_stages;
   uint32_t boxA_bytes, boxB_bytes, stage_bytes;
   float* dw;
+  float* partial;        // split-K partial tiles [tile][split][128][pitch] (nullptr: splits == 1, add into dw)
+  int pitch;             // boxes_per_cta * ckB
   TapEntry taps[kMaxTaps];
 };
 
@@ -414,27 +496,45 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       mbar_wait(&acc_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      for (int x = 0; x < nboxes; ++x) {
-        const int id = box0 + x;
-        const int t = id / p.c_chunks;
-        const int cc = id - t * p.c_chunks;
-        const int tap = p.taps[t].b_tap;
-        const int cbase = cc * p.ckB;
-        float* dst = p.dw + (static_cast<long long>(k) * p.taps_total + tap) * p.C + cbase;
-        for (int c0 = 0; c0 < p.ckB; c0 += 16) {
+      if (p.partial != nullptr) {
+        // split-K: plain stores of this CTA's fp32 tile; conv_wgrad_reduce_kernel sums the splits into dw
+        float* dst = p.partial + ((static_cast<long long>(tile) * p.splits + split) * kTileM + (q * 32 + lane)) * p.pitch;
+        const int ncols = nboxes * p.ckB;
+        for (int c0 = 0; c0 < ncols; c0 += 16) {
           uint32_t v[16];
-          tmem_ld16(taddr + x * p.ckB + c0, v);
+          tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
           if (row_ok) {
-            if (cbase + c0 + 16 <= p.C && (p.C & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                red_add_v4(dst + c0 + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-            } else {
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float4*>(dst + c0 + 4 * i) =
+                  make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                              __uint_as_float(v[4 * i + 3]));
+          }
+        }
+      } else {
+        for (int x = 0; x < nboxes; ++x) {
+          const int id = box0 + x;
+          const int t = id / p.c_chunks;
+          const int cc = id - t * p.c_chunks;
+          const int tap = p.taps[t].b_tap;
+          const int cbase = cc * p.ckB;
+          float* dst = p.dw + (static_cast<long long>(k) * p.taps_total + tap) * p.C + cbase;
+          for (int c0 = 0; c0 < p.ckB; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + x * p.ckB + c0, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              if (cbase + c0 + 16 <= p.C && (p.C & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (cbase + c0 + i < p.C) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+                for (int i = 0; i < 4; ++i)
+                  red_add_v4(dst + c0 + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (cbase + c0 + i < p.C) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+              }
             }
           }
         }
@@ -447,6 +547,35 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// dw[k][tap][c] += sum over splits of the partial tiles (deterministic order); one thread per 4 channels
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                                int K_out, int taps, int C, int ckB, int c_chunks,
+                                                                int boxes_per_cta, int k_tiles, int splits, int pitch) {
+  const int c4n = C >> 2;
+  const long long total = static_cast<long long>(K_out) * taps * c4n;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % c4n) * 4;
+    const int tap = static_cast<int>((idx / c4n) % taps);
+    const int k = static_cast<int>(idx / (static_cast<long long>(c4n) * taps));
+    const int k_tile = k / kTileM, row = k - k_tile * kTileM;
+    const int cc = c / ckB;
+    const int id = tap * c_chunks + cc;
+    const int cgroup = id / boxes_per_cta, x = id - cgroup * boxes_per_cta;
+    const int tile = cgroup * k_tiles + k_tile;
+    const float* src = partial + ((static_cast<long long>(tile) * splits) * kTileM + row) * pitch + x * ckB + (c - cc * ckB);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s2 = 0; s2 < splits; ++s2) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(s2) * kTileM * pitch));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(dw + (static_cast<long long>(k) * taps + tap) * C + c);
+    float4 cur = *o;
+    cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+    *o = cur;
   }
 }
 
@@ -552,7 +681,11 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   // keep every stage 1024B aligned (128B-swizzle atoms are 1024B)
   uint32_t stage = p.a_bytes + p.b_bytes;
   if (stage % 1024) { p.b_bytes += 1024 - stage % 1024; stage = p.a_bytes + p.b_bytes; }
-  p.num_stages = kSmemBudget / (int)stage;
+  // dense bf16 outputs with 64-channel granularity go out through shared memory + TMA store
+  p.tma_store = (L.os == 1 && !L.out_fp32 && (p.block_n % 64) == 0 && (L.Nout % p.block_n) == 0 && L.ldo == L.Nout &&
+                 L.OH == L.I && L.OW == L.J && L.oh0 == 0 && L.ow0 == 0) ? 1 : 0;
+  const int epi_bytes = p.tma_store ? kTileM * p.block_n * 2 : 0;
+  p.num_stages = (kSmemBudget - epi_bytes) / (int)stage;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (p.num_stages < 2) p.num_stages = 2;
   p.OH = L.OH; p.OW = L.OW; p.os = L.os; p.oh0 = L.oh0; p.ow0 = L.ow0; p.ldo = L.ldo;
@@ -569,12 +702,23 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   rc = encode_tiled3(&tmB, L.wmat, L.SC, L.wtaps, L.Nout, p.ck, 1, p.block_n);
   if (rc) return rc;
 
-  const int smem_bytes = p.num_stages * (int)stage + 1024;
+  CUtensorMap tmC, tmR;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmR, 0, sizeof(tmR));
+  if (p.tma_store) {
+    rc = encode_tiled2(&tmC, L.out, L.ldo, (long long)p.M_total, 64, kTileM);
+    if (rc) return rc;
+    if (L.res != nullptr) {
+      rc = encode_tiled2(&tmR, L.res, L.ldo, (long long)p.M_total, 64, kTileM);
+      if (rc) return rc;
+    }
+  }
+  const int smem_bytes = p.num_stages * (int)stage + epi_bytes + 1024;
   rc = set_smem_attr((const void*)conv_igemm_kernel, smem_bytes);
   if (rc) return rc;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
   B200_CHECK_LAUNCH("conv_igemm_kernel");
   return B200_OK;
 }
@@ -686,8 +830,13 @@ extern "C" int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const vo
   return B200_OK;
 }
 
-extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, float* dw,
-                               b200_stream_t stream_) {
+extern "C" size_t b200_conv_wgrad_workspace_bytes(void) {
+  // splits * tiles <= SM count, each partial tile is 128 x 512 fp32
+  return static_cast<size_t>(sm_count() + 8) * kTileM * 512 * sizeof(float);
+}
+
+extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
+                               size_t workspace_bytes, b200_stream_t stream_) {
   int rc = check_desc(d);
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -711,7 +860,7 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   p.col_groups = (p.total_boxes + p.boxes_per_cta - 1) / p.boxes_per_cta;
   p.total_blocks = (p.M_total + p.bk - 1) / p.bk;
   const int tiles = p.k_tiles * p.col_groups;
-  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  int splits = sm_count() / tiles;  // one wave: a CTA owns the whole TMEM, two cannot share an SM
   if (splits > p.total_blocks) splits = p.total_blocks;
   if (splits < 1) splits = 1;
   p.blocks_per_split = (p.total_blocks + splits - 1) / splits;
@@ -724,6 +873,16 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (p.num_stages < 2) p.num_stages = 2;
   p.dw = dw;
+  p.pitch = p.boxes_per_cta * p.ckB;
+  p.partial = nullptr;
+  if (p.splits > 1) {
+    const size_t need = static_cast<size_t>(tiles) * p.splits * kTileM * p.pitch * sizeof(float);
+    B200_REQUIRE(workspace != nullptr && workspace_bytes >= need, B200_ERR_INVALID,
+                 "conv_wgrad: workspace too small (%zu < %zu); see b200_conv_wgrad_workspace_bytes()", workspace_bytes,
+                 need);
+    B200_REQUIRE((d->C & 3) == 0, B200_ERR_UNSUPPORTED, "conv_wgrad: C must be a multiple of 4");
+    p.partial = static_cast<float*>(workspace);
+  }
   for (int r = 0; r < d->R; ++r)
     for (int s = 0; s < d->S; ++s) {
       TapEntry& t = p.taps[r * d->S + s];
@@ -743,5 +902,14 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   const int grid = tiles * p.splits;
   conv_wgrad_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmDy, tmX, p);
   B200_CHECK_LAUNCH("conv_wgrad_kernel");
+  if (p.partial != nullptr) {
+    const long long total = static_cast<long long>(d->K) * p.taps_total * (d->C / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    conv_wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p.partial, dw, d->K, p.taps_total, d->C, p.ckB,
+                                                                          p.c_chunks, p.boxes_per_cta, p.k_tiles, p.splits,
+                                                                          p.pitch);
+    B200_CHECK_LAUNCH("conv_wgrad_reduce_kernel");
+  }
   return B200_OK;
 }

@@ -177,7 +177,7 @@ class Runtime(object):
             buf.data = buf.data.to(device)
         self._anchor = self.arena.slots[0].param
         self._max_c = max([m.num_features for m in model.modules() if isinstance(m, nn.BatchNorm2d)] + [8])
-        self._ws = torch.empty(ops.bn_workspace_floats(self._max_c), device=device, dtype=torch.float32)
+        self._ws = torch.zeros(ops.bn_workspace_floats(self._max_c), device=device, dtype=torch.float32)
         self.loss_scale_inv = 1.0
         self._build()
 
@@ -229,12 +229,13 @@ class Runtime(object):
         return u
 
     def _bn_bwd(self, u, dy, y_mask, act, want_g=False):
-        """BN (+activation) backward of unit u: returns dz (and g = dy*act'(y) when want_g)."""
-        ops.bn_bwd_reduce(dy, y_mask if act != ACT_NONE else None, u.z, act, u.mean, u.invstd, u.sums,
-                          u.bn.dgamma, u.bn.dbeta, self._ws)
+        """BN (+activation) backward of unit u: returns dz (and g = dy*act'(.) when want_g).
+        y_mask=None with an activation: the mask is recomputed from z inside the kernels (no read of y)."""
+        bn = u.bn
+        ops.bn_bwd_reduce(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, bn.dgamma, bn.dbeta,
+                          self._ws)
         g = torch.empty_like(dy) if want_g else None
-        dz = ops.bn_bwd_dx(dy, y_mask if act != ACT_NONE else None, u.z, act, u.mean, u.invstd, u.bn.gamma, u.sums,
-                           g_out=g)
+        dz = ops.bn_bwd_dx(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, g_out=g)
         return dz, g
 
     def _conv_bwd(self, u, dz, need_dx=True, residual=None):
@@ -361,7 +362,7 @@ class ResNetRuntime(Runtime):
         u = st['unit']
         if self.has_maxpool:
             dy = ops.maxpool_bwd(dy, st['argmax'], tuple(u.y.shape))
-        dz, _ = self._bn_bwd(u, dy, u.y, ACT_RELU)
+        dz, _ = self._bn_bwd(u, dy, None, ACT_RELU)
         K, Cin = self.stem_conv.out_channels, st['cin']
         if self.imagenet_stem:
             dws = torch.zeros((K, 16, 16), device=self.device, dtype=torch.float32)
@@ -402,10 +403,10 @@ class ResNetRuntime(Runtime):
             skip = g
         d = self._conv_bwd(last, dz)
         for u in reversed(units[1:-1]):
-            dz, _ = self._bn_bwd(u, d, u.y, ACT_RELU)
+            dz, _ = self._bn_bwd(u, d, None, ACT_RELU)
             d = self._conv_bwd(u, dz)
         u = units[0]
-        dz, _ = self._bn_bwd(u, d, u.y, ACT_RELU)
+        dz, _ = self._bn_bwd(u, d, None, ACT_RELU)
         return self._conv_bwd(u, dz, residual=skip)
 
     # ---- whole network ------------------------------------------------------------------------------

@@ -36,7 +36,8 @@ _ep = ctypes.POINTER(Epilogue)
 SIGNATURES = {
     "b200_conv_fprop": [_dp, _vp, _vp, _vp, _ep, _vp],
     "b200_conv_dgrad": [_dp, _vp, _vp, _vp, _vp, _vp],
-    "b200_conv_wgrad": [_dp, _vp, _vp, _vp, _vp],
+    "b200_conv_wgrad": [_dp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "b200_conv_wgrad_workspace_bytes": [],
     "b200_dwconv_fprop": [_dp, _vp, _vp, _vp, _vp],
     "b200_dwconv_dgrad": [_dp, _vp, _vp, _vp, _vp],
     "b200_dwconv_wgrad": [_dp, _vp, _vp, _vp, _vp, _sz, _vp],
@@ -44,8 +45,8 @@ SIGNATURES = {
     "b200_bn_stats": [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_bn_eval_coeffs": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp],
     "b200_bn_apply": [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
-    "b200_bn_bwd_reduce": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "b200_bn_bwd_dx": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200_bn_bwd_reduce": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200_bn_bwd_dx": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_maxpool3x3s2_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "b200_maxpool3x3s2_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b200_avgpool_fwd": [_vp, _i, _i, _i, _vp, _vp],
@@ -65,6 +66,7 @@ SIGNATURES = {
     "b200_launch_count": [],
 }
 _RESTYPES = {"b200_last_error": ctypes.c_char_p, "b200_launch_count": ctypes.c_longlong,
+             "b200_conv_wgrad_workspace_bytes": ctypes.c_size_t,
              "b200_bn_workspace_floats": ctypes.c_size_t}
 
 _lib = None

@@ -114,12 +114,25 @@ def conv_dgrad(dy, wt, desc, out=None, residual=None):
     return out
 
 
+_WGRAD_WS = {}
+
+
+def _wgrad_workspace(device):
+    """per-device split-K scratch (allocated once; the library states its size)."""
+    ws = _WGRAD_WS.get(device)
+    if ws is None:
+        ws = torch.empty(int(_l.load().b200_conv_wgrad_workspace_bytes()), device=device, dtype=torch.uint8)
+        _WGRAD_WS[device] = ws
+    return ws
+
+
 def conv_wgrad(x, dy, desc, dw):
     """dw [K,R*S,C] fp32 += dy^T (*) x."""
     _chk(x, bf16, "x"); _chk(dy, bf16, "dy"); _chk(dw, torch.float32, "dw")
+    ws = _wgrad_workspace(x.device)
     with _T('conv_wgrad', _conv_flops(desc), 0):
-        _l.check(_l.load().b200_conv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _stream()),
-                 "b200_conv_wgrad")
+        _l.check(_l.load().b200_conv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _stream()), "b200_conv_wgrad")
     return dw
 
 
@@ -185,25 +198,27 @@ def bn_apply(z, scale, shift, act=ACT_NONE, residual=None, z2=None, scale2=None,
     return out
 
 
-def bn_bwd_reduce(dy, y, z, act, mean, invstd, sums, dgamma_acc, dbeta_acc, workspace):
+def bn_bwd_reduce(dy, y, z, act, mean, invstd, gamma, beta, sums, dgamma_acc, dbeta_acc, workspace):
+    """y=None: the activation mask is recomputed from z (valid when nothing was added before the activation)."""
     C = z.shape[-1]
     M = z.numel() // C
     _chk(dy, bf16, "dy"); _chk(y, bf16, "y"); _chk(z, bf16, "z")
     with _T('bn_bwd_reduce', 0, 2 * z.numel() * (2 + (y is not None))):
         _l.check(_l.load().b200_bn_bwd_reduce(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
-                                              invstd.data_ptr(), sums.data_ptr(), _l.ptr(dgamma_acc), _l.ptr(dbeta_acc),
-                                              workspace.data_ptr(), _stream()), "b200_bn_bwd_reduce")
+                                              invstd.data_ptr(), _l.ptr(gamma), _l.ptr(beta), sums.data_ptr(),
+                                              _l.ptr(dgamma_acc), _l.ptr(dbeta_acc), workspace.data_ptr(), _stream()),
+                 "b200_bn_bwd_reduce")
 
 
-def bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, sums, dz=None, g_out=None):
+def bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, beta, sums, dz=None, g_out=None):
     C = z.shape[-1]
     M = z.numel() // C
     if dz is None:
         dz = torch.empty_like(z)
     with _T('bn_bwd_dx', 0, 2 * z.numel() * (3 + (y is not None) + (g_out is not None))):
         _l.check(_l.load().b200_bn_bwd_dx(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
-                                          invstd.data_ptr(), _l.ptr(gamma), sums.data_ptr(), dz.data_ptr(),
-                                          _l.ptr(g_out), _stream()), "b200_bn_bwd_dx")
+                                          invstd.data_ptr(), _l.ptr(gamma), _l.ptr(beta), sums.data_ptr(),
+                                          dz.data_ptr(), _l.ptr(g_out), _stream()), "b200_bn_bwd_dx")
     return dz
 
 

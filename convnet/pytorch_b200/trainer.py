@@ -51,6 +51,32 @@ def _average_duplicates(outputs, target, batch_first=True):
     return outputs.view(-1, bsz, *outputs.shape[1:]).mean(dim=0)
 
 
+def _cuda_prefetch(loader, device, dtype):
+    """Yield device-resident batches one step ahead: batch i+1 is copied host->device on a side stream while
+    step i computes (the reference issues a blocking copy at the top of every step, trainer.py:116-117)."""
+    copy_stream = torch.cuda.Stream(device=device)
+    pending = None
+    for inputs, target in loader:
+        with torch.cuda.stream(copy_stream):
+            nxt_x = inputs.to(device, dtype=dtype, non_blocking=True)
+            nxt_y = target.to(device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        if pending is not None:
+            px, py, ev = pending
+            torch.cuda.current_stream(device).wait_event(ev)
+            px.record_stream(torch.cuda.current_stream(device))
+            py.record_stream(torch.cuda.current_stream(device))
+            yield px, py
+        pending = (nxt_x, nxt_y, ready)
+    if pending is not None:
+        px, py, ev = pending
+        torch.cuda.current_stream(device).wait_event(ev)
+        px.record_stream(torch.cuda.current_stream(device))
+        py.record_stream(torch.cuda.current_stream(device))
+        yield px, py
+
+
 class Trainer(object):
     def __init__(self, model, criterion, optimizer=None, device_ids=[0], device='cuda', dtype=torch.float,
                  distributed=False, local_rank=-1, adapt_grad_norm=None, mixup=None, cutmix=None,
@@ -192,7 +218,9 @@ class Trainer(object):
         except TypeError:
             n_batches = -1
         tick = time.time()
-        for i, (inputs, target) in enumerate(data_loader):
+        batches = _cuda_prefetch(data_loader, self.device, self._input_dtype()) \
+            if (self.b200 is not None and chunk_batch == 1) else data_loader
+        for i, (inputs, target) in enumerate(batches):
             duplicates = inputs.dim() > 4  # B x D x C x H x W
             if training and duplicates and self.adapt_grad_norm is not None and i % self.adapt_grad_norm == 0:
                 per_copy = sum(float(self._grad_norm(inputs.select(1, j), target)) for j in range(inputs.size(1)))

@@ -67,9 +67,12 @@ int b200_conv_fprop(const b200_conv_desc* d, const void* x, const void* w, void*
 /* wt is the bf16 weight re-laid as [C][R*S][K]; residual (bf16, shape of dx) may be NULL */
 int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* wt, void* dx,
                     const void* residual, b200_stream_t stream);
-/* dw fp32 [K][R*S][C]; ACCUMULATES (dw += ...) so that gradient accumulation works */
+/* dw fp32 [K][R*S][C]; ACCUMULATES (dw += ...) so that gradient accumulation works.  Split-K over the
+ * pixels: partial tiles go to `workspace` (b200_conv_wgrad_workspace_bytes() bytes, any content) and are
+ * summed in a fixed order by a second kernel, so the result is deterministic. */
+size_t b200_conv_wgrad_workspace_bytes(void);
 int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, float* dw,
-                    b200_stream_t stream);
+                    void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
 /* ---- depthwise 3x3 convolution, CUDA-core HBM-bound kernels (csrc/dwconv.cu) -------------------
  * replaces nn.Conv2d(groups=C) fwd/bwd (models/mobilenet_v2.py:57-58). w/dw are [R*S][C]. */
@@ -96,15 +99,18 @@ int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const floa
 int b200_bn_apply(const void* z, long long M, int C, const float* scale, const float* shift,
                   const void* residual, const void* z2, const float* scale2, const float* shift2,
                   int act, void* y, b200_stream_t stream);
-/* g = dy * act'(y); dgamma/dbeta: per-layer sums written to sums[0..C) (dgamma) sums[C..2C) (dbeta)
- * and ACCUMULATED into dgamma_acc/dbeta_acc (gradient arena). y may be NULL when act == NONE. */
+/* g = dy * act'(a) where a = y when y != NULL (needed when a residual was added before the activation),
+ * else a is recomputed as z*gamma*invstd + (beta - mean*gamma*invstd), which saves reading y.
+ * dgamma/dbeta: per-layer sums written to sums[0..C) (dgamma) sums[C..2C) (dbeta) and ACCUMULATED into
+ * dgamma_acc/dbeta_acc (gradient arena).  The workspace must be zero before its first use (the kernels
+ * leave it zeroed) and must not be shared between concurrently running streams. */
 int b200_bn_bwd_reduce(const void* dy, const void* y, const void* z, long long M, int C, int act,
-                       const float* mean, const float* invstd, float* sums, float* dgamma_acc,
-                       float* dbeta_acc, float* workspace, b200_stream_t stream);
+                       const float* mean, const float* invstd, const float* gamma, const float* beta,
+                       float* sums, float* dgamma_acc, float* dbeta_acc, float* workspace, b200_stream_t stream);
 /* dz = gamma*invstd*(g - dbeta/M - xhat*dgamma/M); optionally also writes g (bf16) for the skip path */
 int b200_bn_bwd_dx(const void* dy, const void* y, const void* z, long long M, int C, int act,
-                   const float* mean, const float* invstd, const float* gamma, const float* sums,
-                   void* dz, void* g_out, b200_stream_t stream);
+                   const float* mean, const float* invstd, const float* gamma, const float* beta,
+                   const float* sums, void* dz, void* g_out, b200_stream_t stream);
 
 /* ---- pooling (csrc/pool.cu) -------------------------------------------------------------------
  * replaces nn.MaxPool2d(3,2,1) (models/resnet.py:230) and nn.AdaptiveAvgPool2d(1) (resnet.py:241) */

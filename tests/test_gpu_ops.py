@@ -37,7 +37,7 @@ def test_bn_forward_backward(M, C, act):
     rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
     nbt = torch.zeros((), dtype=torch.int64).cuda()
     mean, invstd, scale, shift = [torch.empty(C).cuda() for _ in range(4)]
-    ws = torch.empty(ops.bn_workspace_floats(C)).cuda()
+    ws = torch.zeros(ops.bn_workspace_floats(C)).cuda()
     res = torch.randn(M, C, generator=g).cuda().to(bf16)
     ops.bn_stats(z, gamma, beta, 1e-5, 0.1, rm, rv, nbt, mean, invstd, scale, shift, ws)
     y = ops.bn_apply(z, scale, shift, act, residual=res)
@@ -61,9 +61,9 @@ def test_bn_forward_backward(M, C, act):
     gd = dy.double() * mask
     sums = torch.empty(2 * C).cuda()
     dgam, dbet = torch.zeros(C).cuda(), torch.zeros(C).cuda()
-    ops.bn_bwd_reduce(dy, y, z, act, mean, invstd, sums, dgam, dbet, ws)
+    ops.bn_bwd_reduce(dy, y, z, act, mean, invstd, gamma, beta, sums, dgam, dbet, ws)
     gout = torch.empty_like(dy)
-    dz = ops.bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, sums, g_out=gout)
+    dz = ops.bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, beta, sums, g_out=gout)
     torch.cuda.synchronize()
     (pre_lin := xhat * gamma.double() + beta.double())
     dzd, dgam_ref, dbet_ref = torch.autograd.grad(pre_lin, [zd, ], gd, retain_graph=True)[0], \
@@ -74,7 +74,7 @@ def test_bn_forward_backward(M, C, act):
     assert close_bf16(dz, dzd)
     assert close_bf16(gout, gd)
     # accumulate semantics of dgamma/dbeta
-    ops.bn_bwd_reduce(dy, y, z, act, mean, invstd, sums, dgam, dbet, ws)
+    ops.bn_bwd_reduce(dy, y, z, act, mean, invstd, gamma, beta, sums, dgam, dbet, ws)
     torch.cuda.synchronize()
     assert rel(dgam, 2 * dgam_ref) < tol
 
@@ -103,7 +103,7 @@ def test_bn_cumulative_momentum():
     C = 32
     rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
     nbt = torch.zeros((), dtype=torch.int64).cuda()
-    ws = torch.empty(ops.bn_workspace_floats(C)).cuda()
+    ws = torch.zeros(ops.bn_workspace_floats(C)).cuda()
     bn = torch.nn.BatchNorm2d(C, momentum=None).double()
     bufs = [torch.empty(C).cuda() for _ in range(4)]
     for i in range(3):
