@@ -11,6 +11,7 @@
 // the workspace.  The workspace must be zero before first use and must not be shared by concurrent streams.
 #include "common.cuh"
 #include "host.h"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -33,7 +34,8 @@ static inline int reduce_blocks(long long M, int C, const RowMap& rm) {
   long long want = (iters + 7) / 8;          // >= 8 row-iterations per block
   long long cap = 400000LL / (2 * C);        // bound the number of fp64 atomics (blocks * 2C)
   if (cap < sm_count()) cap = sm_count();
-  if (cap > kBnMaxBlocks) cap = kBnMaxBlocks;
+  static const int per_sm = getenv("B200_BN_REDUCE_BLOCKS_PER_SM") ? atoi(getenv("B200_BN_REDUCE_BLOCKS_PER_SM")) : 3;
+  if (cap > per_sm * sm_count()) cap = per_sm * sm_count();  // few, fat blocks: less same-address atomic traffic at the end
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;
@@ -48,6 +50,10 @@ static inline int stream_blocks(long long M, const RowMap& rm) {
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
@@ -111,14 +117,18 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   if (active) {
     long long r = row_begin + r0;
-    for (; r + 3LL * rows_per_iter < row_end; r += 4LL * rows_per_iter) {
-      float f[4][8];
+    for (; r + 7LL * rows_per_iter < row_end; r += 8LL * rows_per_iter) {
+      uint4 raw[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) load8(z + (r + (long long)u * rows_per_iter) * C + v * 8, f[u]);
+      for (int u = 0; u < 8; ++u)
+        raw[u] = *reinterpret_cast<const uint4*>(z + (r + (long long)u * rows_per_iter) * C + v * 8);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u) {
+        float f[8];
+        unpack8(raw[u], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i] += f[u][i]; acc[8 + i] += f[u][i] * f[u][i]; }
+        for (int i = 0; i < 8; ++i) { acc[i] += f[i]; acc[8 + i] += f[i] * f[i]; }
+      }
     }
     for (; r < row_end; r += rows_per_iter) {
       float f[8];
@@ -257,25 +267,30 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
         ms.sh[i] = (beta ? be[i] : 0.f) - mu[i] * ms.sc[i];
       }
     }
-    for (long long r = row_begin + r0; r < row_end; r += 2LL * rows_per_iter) {
-      const long long rb = r + rows_per_iter;
-      const bool hb = rb < row_end;
-      float da[8], db[8], za[8], zb[8], ya[8], yb[8], ga[8], gb[8];
-      load8(dy + r * C + v * 8, da);
-      load8(z + r * C + v * 8, za);
-      if (have_y && act != B200_ACT_NONE) load8(y + r * C + v * 8, ya);
-      if (hb) {
-        load8(dy + rb * C + v * 8, db);
-        load8(z + rb * C + v * 8, zb);
-        if (have_y && act != B200_ACT_NONE) load8(y + rb * C + v * 8, yb);
+    const bool need_y = have_y && act != B200_ACT_NONE;
+    for (long long r = row_begin + r0; r < row_end; r += 4LL * rows_per_iter) {
+      uint4 rd[4], rz[4], ry[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * rows_per_iter;
+        ok[u] = rr < row_end;
+        if (ok[u]) {
+          rd[u] = *reinterpret_cast<const uint4*>(dy + rr * C + v * 8);
+          rz[u] = *reinterpret_cast<const uint4*>(z + rr * C + v * 8);
+          if (need_y) ry[u] = *reinterpret_cast<const uint4*>(y + rr * C + v * 8);
+        }
       }
-      masked_grad(da, za, ya, have_y, act, ms, ga);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { acc[i] += ga[i] * (za[i] - mu[i]) * is[i]; acc[8 + i] += ga[i]; }
-      if (hb) {
-        masked_grad(db, zb, yb, have_y, act, ms, gb);
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        float da[8], za[8], ya[8], ga[8];
+        unpack8(rd[u], da);
+        unpack8(rz[u], za);
+        if (need_y) unpack8(ry[u], ya);
+        masked_grad(da, za, ya, have_y, act, ms, ga);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i] += gb[i] * (zb[i] - mu[i]) * is[i]; acc[8 + i] += gb[i]; }
+        for (int i = 0; i < 8; ++i) { acc[i] += ga[i] * (za[i] - mu[i]) * is[i]; acc[8 + i] += ga[i]; }
       }
     }
   }

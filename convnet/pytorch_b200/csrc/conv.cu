@@ -18,7 +18,8 @@ namespace b200 {
 
 constexpr int kMaxStages = 8;
 constexpr int kMaxTaps = 32;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;        // wgrad: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kIgemmThreads = 320;   // igemm: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int kTileM = 128;
 constexpr uint32_t kTmemCols = 512;
 
@@ -44,6 +45,7 @@ struct IgemmParams {
   int ldo;
   int act, out_fp32;
   int tma_store;         // 1: dense bf16 output staged in smem and written by TMA (tmC), residual via tmR
+  int plain_a;           // 1: A is a dense [M_total, SC] matrix (1x1, stride 1, no padding): tiled TMA
   void* out;
   const void* res;
   const float* bias;
@@ -117,7 +119,7 @@ __device__ __forceinline__ void store_chunk16(const IgemmParams& p, const uint32
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kIgemmThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                   const __grid_constant__ IgemmParams p) {
@@ -142,8 +144,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4);
-    mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], 8);
+    mbar_init(&tmem_empty[1], 8);
     mbar_init(&res_bar, 1);
     fence_mbar_init();
     prefetch_tmap(&tmA);
@@ -187,7 +189,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + p.a_bytes;
             mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
-            tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cc * p.ck, base_w, base_h, img, te.off_w, te.off_h);
+            if (p.plain_a)  // 1x1 / stride 1: the A operand is a dense [M, C] matrix -> tiled TMA (faster than im2col)
+              tma_load_2d(&tmA, &full_bar[stage], sa, cc * p.ck, m0);
+            else
+              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cc * p.ck, base_w, base_h, img, te.off_w, te.off_h);
             tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.ck, te.b_tap, n_tile * p.block_n);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
           }
@@ -227,7 +232,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter take alternate 16-column chunks
     const int IJ = p.I * p.J;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -256,7 +262,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint8_t* epi = smem + p.num_stages * stage_bytes;
         const int nbox = p.block_n >> 6;
         if (leader && local > 0) bulk_wait_group_read0();  // previous tile's store has finished reading smem
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (p.res != nullptr) {
           if (leader) {
             mbar_arrive_expect_tx(&res_bar, static_cast<uint32_t>(nbox) * kTileM * 128u);
@@ -267,7 +273,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
@@ -311,7 +317,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // TMEM stage is free: the MMA warp may start tile+2
         fence_proxy_async();                             // generic-proxy smem writes -> visible to TMA
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (leader) {
           for (int b = 0; b < nbox; ++b)
             tma_store_2d(&tmC, epi + b * (kTileM * 128), nbase + b * 64, m_tile * kTileM);
@@ -321,16 +327,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      int c0 = 0;
-      for (; c0 + 32 <= p.block_n; c0 += 32) {
-        uint32_t v0[16], v1[16];
-        tmem_ld16(taddr + c0, v0);
-        tmem_ld16(taddr + c0 + 16, v1);
-        tmem_ld_wait();
-        store_chunk16(p, v0, off, nbase + c0, row_ok && (nbase + c0 < p.N_total));
-        store_chunk16(p, v1, off, nbase + c0 + 16, row_ok && (nbase + c0 + 16 < p.N_total));
-      }
-      for (; c0 < p.block_n; c0 += 16) {
+      for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
         uint32_t v0[16];
         tmem_ld16(taddr + c0, v0);
         tmem_ld_wait();
@@ -370,6 +367,7 @@ struct WgradParams {
   int num_stages;
   uint32_t boxA_bytes, boxB_bytes, stage_bytes;
   float* dw;
+  int plain_x;           // 1: x is a dense [M_total, C] matrix (1x1 stride 1): tiled TMA instead of im2col
   float* partial;        // split-K partial tiles [tile][split][128][pitch] (nullptr: splits == 1, add into dw)
   int pitch;             // boxes_per_cta * ckB
   TapEntry taps[kMaxTaps];
@@ -454,8 +452,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             const int t = id / p.c_chunks;
             const int cc = id - t * p.c_chunks;
             const TapEntry te = p.taps[t];
-            tma_load_im2col_4d(&tmX, &full_bar[stage], sb + x * p.boxB_bytes, cc * p.ckB, base_w, base_h, img,
-                               te.off_w, te.off_h);
+            if (p.plain_x)
+              tma_load_2d(&tmX, &full_bar[stage], sb + x * p.boxB_bytes, cc * p.ckB, pix0);
+            else
+              tma_load_im2col_4d(&tmX, &full_bar[stage], sb + x * p.boxB_bytes, cc * p.ckB, base_w, base_h, img,
+                                 te.off_w, te.off_h);
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -696,8 +697,14 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   const int upper_w = L.lower_w + (L.J - 1) * L.trav + 1 - L.SW;
   const int upper_h = L.lower_h + (L.I - 1) * L.trav + 1 - L.SH;
   CUtensorMap tmA, tmB;
-  int rc = encode_im2col(&tmA, L.src, L.Nimg, L.SH, L.SW, L.SC, p.ck, kTileM, L.lower_w, L.lower_h, upper_w,
-                         upper_h, L.trav);
+  int rc;
+  p.plain_a = (L.ntaps == 1 && L.trav == 1 && L.lower_w == 0 && L.lower_h == 0 && L.taps[0].off_w == 0 &&
+               L.taps[0].off_h == 0 && L.I == L.SH && L.J == L.SW) ? 1 : 0;
+  if (p.plain_a)
+    rc = encode_tiled2(&tmA, L.src, L.SC, (long long)p.M_total, p.ck, kTileM);
+  else
+    rc = encode_im2col(&tmA, L.src, L.Nimg, L.SH, L.SW, L.SC, p.ck, kTileM, L.lower_w, L.lower_h, upper_w, upper_h,
+                       L.trav);
   if (rc) return rc;
   rc = encode_tiled3(&tmB, L.wmat, L.SC, L.wtaps, L.Nout, p.ck, 1, p.block_n);
   if (rc) return rc;
@@ -718,7 +725,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (rc) return rc;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  conv_igemm_kernel<<<grid, kIgemmThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
   B200_CHECK_LAUNCH("conv_igemm_kernel");
   return B200_OK;
 }
@@ -850,7 +857,7 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   p.K_out = d->K; p.C = d->C; p.taps_total = d->R * d->S;
   p.ckA = pick_ck(d->K);
   p.ckB = pick_ck(d->C);
-  p.bk = 32;
+  p.bk = 64;  // pixels per TMA box: fewer, larger TMA requests per byte (32-pixel boxes were request-rate bound)
   p.c_chunks = (d->C + p.ckB - 1) / p.ckB;
   p.total_boxes = p.taps_total * p.c_chunks;
   p.boxes_per_cta = 512 / p.ckB;
@@ -893,8 +900,13 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   if (rc) return rc;
   const int upper_w = p.lower_w + (d->Q - 1) * d->stride + 1 - d->W;
   const int upper_h = p.lower_h + (d->P - 1) * d->stride + 1 - d->H;
-  rc = encode_im2col(&tmX, x, d->N, d->H, d->W, d->C, p.ckB, p.bk, p.lower_w, p.lower_h, upper_w, upper_h,
-                     d->stride);
+  p.plain_x = (d->R == 1 && d->S == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && d->P == d->H &&
+               d->Q == d->W) ? 1 : 0;
+  if (p.plain_x)
+    rc = encode_tiled2(&tmX, x, d->C, (long long)p.M_total, p.ckB, p.bk);
+  else
+    rc = encode_im2col(&tmX, x, d->N, d->H, d->W, d->C, p.ckB, p.bk, p.lower_w, p.lower_h, upper_w, upper_h,
+                       d->stride);
   if (rc) return rc;
   const int smem_bytes = p.num_stages * (int)p.stage_bytes + 1024;
   rc = set_smem_attr((const void*)conv_wgrad_kernel, smem_bytes);

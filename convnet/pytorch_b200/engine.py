@@ -246,6 +246,52 @@ class Runtime(object):
         wt = ops.weight_transpose(u.conv.w16)
         return ops.conv_dgrad(dz, wt, u.desc, residual=residual)
 
+    # ---- classifier head: global average pool -> (dropout) -> linear as a 1x1 conv on a 1x1 map ----------
+    def _head_build(self, fc, dropout_p=0.0):
+        a = self.arena
+        sw, sb = a.slot(fc.weight), a.slot(fc.bias)
+        self.classes = fc.out_features
+        self.classes_pad = _round_up(self.classes, 8)
+        self.fc_in = fc.in_features
+        self.fc_w16 = a.kernel_view(a.p16, sw)       # [Kpad,1,C]
+        self.fc_gw = a.kernel_view(a.g32, sw)
+        self.fc_b = a.kernel_view(a.p32, sb)         # [Kpad]
+        self.fc_gb = a.kernel_view(a.g32, sb)
+        self.dropout_p = float(dropout_p)
+
+    def _head_fwd(self, h, training, want_tape):
+        N = h.shape[0]
+        feat = ops.avgpool_fwd(h)                                        # [N,1,1,C]
+        mask = None
+        if training and self.dropout_p > 0:
+            # the Bernoulli draw uses torch's CUDA generator (RNG glue on a [N, C] tensor; mobilenet_v2.py:126)
+            keep = 1.0 - self.dropout_p
+            mask = (torch.rand(feat.shape, device=self.device) < keep).to(torch.bfloat16) / keep
+            feat = feat * mask
+        desc = ops.make_desc(N, 1, 1, self.fc_in, self.classes_pad, 1, 1, 1, 0)
+        logits = ops.conv_fprop(feat, self.fc_w16, desc, bias=self.fc_b, out_fp32=True).view(N, self.classes_pad)
+        out = logits if self.classes_pad == self.classes else logits[:, :self.classes]
+        tape = {'feat': feat, 'mask': mask, 'last_shape': tuple(h.shape), 'fc_desc': desc} if want_tape else None
+        return out, tape
+
+    def _head_bwd(self, tape, dlogits):
+        N = dlogits.shape[0]
+        if self.classes_pad == self.classes:
+            dl = torch.empty((N, self.classes_pad), device=self.device, dtype=torch.bfloat16)
+            ops.cast_bf16(dlogits.contiguous().float(), dl)
+        else:
+            dl = torch.zeros((N, self.classes_pad), device=self.device, dtype=torch.bfloat16)
+            dl[:, :self.classes].copy_(dlogits)
+        desc = tape['fc_desc']
+        dl4 = dl.view(N, 1, 1, self.classes_pad)
+        ops.colsum_bf16(dl, self.fc_gb)
+        ops.conv_wgrad(tape['feat'], dl4, desc, self.fc_gw)
+        wt = ops.weight_transpose(self.fc_w16)
+        dfeat = ops.conv_dgrad(dl4, wt, desc)
+        if tape['mask'] is not None:
+            dfeat = dfeat * tape['mask']
+        return ops.avgpool_bwd(dfeat, tape['last_shape'])
+
     # ---- autograd glue ----------------------------------------------------------------------------
     def forward(self, x):
         if x.device.type != 'cuda':
@@ -320,15 +366,7 @@ class ResNetRuntime(Runtime):
                 if blk.downsample is not None:
                     spec['down'] = (_Conv(a, blk.downsample[0]), _BN(a, blk.downsample[1]))
                 self.blocks.append(spec)
-        fc = m.fc
-        sw, sb = a.slot(fc.weight), a.slot(fc.bias)
-        self.classes = fc.out_features
-        self.classes_pad = _round_up(self.classes, 8)
-        self.fc_in = fc.in_features
-        self.fc_w16 = a.kernel_view(a.p16, sw)       # [Kpad,1,C]
-        self.fc_gw = a.kernel_view(a.g32, sw)
-        self.fc_b = a.kernel_view(a.p32, sb)         # [Kpad]
-        self.fc_gb = a.kernel_view(a.g32, sb)
+        self._head_build(m.fc)
 
     # ---- stem ---------------------------------------------------------------------------------------
     def _stem_fwd(self, x, training):
@@ -416,39 +454,129 @@ class ResNetRuntime(Runtime):
         for spec in self.blocks:
             h, s = self._block_fwd(spec, h, training)
             saved.append(s if want_tape else None)
-        N = h.shape[0]
-        feat = ops.avgpool_fwd(h)                                        # [N,1,1,C]
-        desc = ops.make_desc(N, 1, 1, self.fc_in, self.classes_pad, 1, 1, 1, 0)
-        logits = ops.conv_fprop(feat, self.fc_w16, desc, bias=self.fc_b, out_fp32=True).view(N, self.classes_pad)
-        out = logits if self.classes_pad == self.classes else logits[:, :self.classes]
-        tape = None
-        if want_tape:
-            tape = {'stem': stem, 'blocks': saved, 'feat': feat, 'last_shape': tuple(h.shape), 'fc_desc': desc}
+        out, head = self._head_fwd(h, training, want_tape)
+        tape = {'stem': stem, 'blocks': saved, 'head': head} if want_tape else None
         return out, tape
 
     def run_backward(self, tape, dlogits):
-        N = dlogits.shape[0]
-        if self.classes_pad == self.classes:
-            dl = torch.empty((N, self.classes_pad), device=self.device, dtype=torch.bfloat16)
-            ops.cast_bf16(dlogits.contiguous().float(), dl)
-        else:
-            dl = torch.zeros((N, self.classes_pad), device=self.device, dtype=torch.bfloat16)
-            dl[:, :self.classes].copy_(dlogits)
-        desc = tape['fc_desc']
-        dl4 = dl.view(N, 1, 1, self.classes_pad)
-        ops.colsum_bf16(dl, self.fc_gb)
-        ops.conv_wgrad(tape['feat'], dl4, desc, self.fc_gw)
-        wt = ops.weight_transpose(self.fc_w16)
-        dfeat = ops.conv_dgrad(dl4, wt, desc)
-        d = ops.avgpool_bwd(dfeat, tape['last_shape'])
+        d = self._head_bwd(tape['head'], dlogits)
         for spec, saved in zip(reversed(self.blocks), reversed(tape['blocks'])):
             d = self._block_bwd(spec, saved, d)
+        self._stem_bwd(tape['stem'], d)
+
+
+class MobileNetRuntime(Runtime):
+    """Pipeline for models.mobilenet_v2.MobileNet_v2: 1x1 expand / depthwise 3x3 / 1x1 project units with
+    BN + ReLU6, identity skips, dropout + linear head (reference: models/mobilenet_v2.py:39-156)."""
+
+    def _build(self):
+        m, a = self.model, self.arena
+        f = m.features
+        conv0 = f.conv0[0]
+        if conv0.kernel_size != (3, 3) or conv0.in_channels > 16 or conv0.groups != 1:
+            raise B200Error('unsupported MobileNet stem')
+        self.stem_conv = conv0
+        s = a.slot(conv0.weight)
+        self.stem_w32 = a.p32[s.offset:s.offset + s.numel]
+        self.stem_g32 = a.g32[s.offset:s.offset + s.numel]
+        self.stem_bn = _BN(a, f.conv0[1])
+        self.blocks = []
+        for name, mod in f.named_children():
+            if not name.startswith('bottleneck'):
+                continue
+            if mod.residual_block is not None:
+                raise B200Error('residual_block is outside the B200 hot path')
+            self.blocks.append({'add_res': mod.add_res, 'units': self._parse_units(list(mod.block))})
+        self.blocks.append({'add_res': False, 'units': self._parse_units(list(f.conv1))})
+        drop, fc = m.classifier[0], m.classifier[1]
+        self._head_build(fc, dropout_p=drop.p if isinstance(drop, nn.Dropout) else 0.0)
+        max_c = max(u[1].C for b in self.blocks for u in b['units'] if u[0] == 'dw')
+        self._dw_ws = torch.empty(592 * 9 * max_c, device=self.device, dtype=torch.float32)
+
+    def _parse_units(self, layers):
+        units, i = [], 0
+        while i < len(layers):
+            conv, bn = layers[i], layers[i + 1]
+            has_act = i + 2 < len(layers) and isinstance(layers[i + 2], (nn.ReLU6, nn.ReLU))
+            act = ACT_NONE
+            if has_act:
+                act = ACT_RELU6 if isinstance(layers[i + 2], nn.ReLU6) else ACT_RELU
+            kind = 'dw' if conv.groups > 1 else 'dense'
+            units.append((kind, _Conv(self.arena, conv), _BN(self.arena, bn), act))
+            i += 3 if has_act else 2
+        return units
+
+    def _mb_unit_fwd(self, x, kind, conv, bn, act, training, residual=None):
+        N, H, W, _ = x.shape
+        u = _Unit()
+        u.conv, u.bn, u.act, u.x = conv, bn, act, x
+        u.desc = conv.desc(N, H, W)
+        u.z = ops.dwconv_fprop(x, conv.w16, u.desc) if kind == 'dw' else ops.conv_fprop(x, conv.w16, u.desc)
+        self._bn_coeffs(u, training)
+        u.y = ops.bn_apply(u.z, u.scale, u.shift, act, residual=residual)
+        return u
+
+    def _mb_conv_bwd(self, kind, u, dz, need_dx=True, residual=None):
+        if kind == 'dw':
+            ops.dwconv_wgrad(u.x, dz, u.desc, u.conv.g32, self._dw_ws)
+            return ops.dwconv_dgrad(dz, u.conv.w16, u.desc) if need_dx else None
+        return self._conv_bwd(u, dz, need_dx=need_dx, residual=residual)
+
+    def _stem_fwd(self, x, training):
+        N, Cin, H, W = x.shape
+        K = self.stem_conv.out_channels
+        xs = ops.input_prep(x.float().contiguous(), 16, s2d=False)
+        ws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.bfloat16)
+        ws[:, :, :Cin].copy_(self.stem_w32.view(K, 9, Cin))
+        st, pad = self.stem_conv.stride[0], self.stem_conv.padding[0]
+        u = _Unit()
+        u.conv, u.bn, u.act, u.x = None, self.stem_bn, ACT_RELU6, xs
+        u.desc = ops.make_desc(N, H, W, 16, K, 3, 3, st, pad)
+        u.z = ops.conv_fprop(xs, ws, u.desc)
+        self._bn_coeffs(u, training)
+        u.y = ops.bn_apply(u.z, u.scale, u.shift, ACT_RELU6)
+        return u.y, {'unit': u, 'cin': Cin}
+
+    def _stem_bwd(self, st, dy):
+        u = st['unit']
+        dz, _ = self._bn_bwd(u, dy, None, ACT_RELU6)
+        K, Cin = self.stem_conv.out_channels, st['cin']
+        dws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.float32)
+        ops.conv_wgrad(u.x, dz, u.desc, dws)
+        self.stem_g32.view(K, 9, Cin).add_(dws[:, :, :Cin])
+
+    def run_forward(self, x, training, want_tape):
+        h, stem = self._stem_fwd(x, training)
+        saved = []
+        for spec in self.blocks:
+            xin, units = h, []
+            for j, (kind, conv, bn, act) in enumerate(spec['units']):
+                last = j == len(spec['units']) - 1
+                u = self._mb_unit_fwd(h, kind, conv, bn, act, training,
+                                      residual=xin if (last and spec['add_res']) else None)
+                units.append(u)
+                h = u.y
+            saved.append(units if want_tape else None)
+        out, head = self._head_fwd(h, training, want_tape)
+        tape = {'stem': stem, 'blocks': saved, 'head': head} if want_tape else None
+        return out, tape
+
+    def run_backward(self, tape, dlogits):
+        d = self._head_bwd(tape['head'], dlogits)
+        for spec, units in zip(reversed(self.blocks), reversed(tape['blocks'])):
+            skip = d if spec['add_res'] else None   # out = bn(z) + x (no activation): the skip gradient is dy itself
+            for j in range(len(units) - 1, -1, -1):
+                kind, _, _, act = spec['units'][j]
+                u = units[j]
+                dz, _ = self._bn_bwd(u, d, None, act)
+                d = self._mb_conv_bwd(kind, u, dz, residual=skip if j == 0 else None)
         self._stem_bwd(tape['stem'], d)
 
 
 def convert_b200(model, device=None):
     """Convert a registry model for the B200 kernel path (in place) and return it."""
     from .models.resnet import ResNet
+    from .models.mobilenet_v2 import MobileNet_v2
     from . import lib
     lib.load()  # fail loudly when the CUDA extension is missing
     if not torch.cuda.is_available():
@@ -458,6 +586,8 @@ def convert_b200(model, device=None):
         return model
     if isinstance(model, ResNet):
         rt = ResNetRuntime(model, device)
+    elif isinstance(model, MobileNet_v2):
+        rt = MobileNetRuntime(model, device)
     else:
         raise B200Error('no B200 runtime for model type %s yet' % type(model).__name__)
     object.__setattr__(model, '_b200', rt)

@@ -126,6 +126,9 @@ def _check_against_bf16_oracle(mine, ref, x, y, logit_tol=2e-3, grad_tol=1.5e-2,
     assert abs(float(loss) - float(o_loss)) < 5e-3
     gm = torch.cat([p.grad.cpu().flatten() for _, p in mine.named_parameters()])
     go = torch.cat([o_grads[n].flatten() for n, _ in mine.named_parameters()])
+    worst = sorted(((_rel(p.grad.cpu(), o_grads[n]), n) for n, p in mine.named_parameters()
+                    if float(o_grads[n].norm()) > 0), reverse=True)[:5]
+    print('T2 logits rel %.3e grad rel %.3e worst %s' % (_rel(lo.cpu(), o_logits), _rel(gm, go), worst))
     assert _rel(gm, go) < grad_tol, 'global grad rel vs bf16 oracle %.3e' % _rel(gm, go)
     for n, p in mine.named_parameters():
         if float(o_grads[n].norm()) > 0:
@@ -201,3 +204,55 @@ def test_state_dict_roundtrip_with_reference_layout():
     b.load_state_dict(sd)
     for k, v in b.state_dict().items():
         assert v.shape == sd[k].shape and torch.equal(v.cpu().float(), sd[k].float()), k
+
+
+def _emulate_bf16_storage(model):
+    """straight-through bf16 rounding after every conv / BN / activation / pooling output of a torch model:
+    the storage precision of the kernel pipeline (cf. oracle.ref_model, which does the same for ResNets)."""
+    import torch.nn as nn
+    from oracle.ref_model import _STRound
+    kinds = (nn.Conv2d, nn.BatchNorm2d, nn.ReLU, nn.ReLU6, nn.AdaptiveAvgPool2d, nn.MaxPool2d)
+    for m in model.modules():
+        if isinstance(m, kinds):
+            if isinstance(m, (nn.ReLU, nn.ReLU6)):
+                m.inplace = False
+            m.register_forward_hook(lambda mod, inp, out: _STRound.apply(out))
+    return model
+
+
+def test_mobilenet_v2_step():
+    """MobileNet-v2 (depthwise path) vs stock torch: fp32 (T1, loose) and with bf16 storage emulated by hooks (T2).
+    Dropout is disabled so that both sides see the same network."""
+    from convnet.pytorch_b200.models import mobilenet_v2
+
+    def factory(**cfg):
+        m = mobilenet_v2(**cfg)
+        m.classifier[0].p = 0.0
+        return m
+    ref, mine, x, y = _pair(factory, dict(dataset='imagenet'), (3, 96, 96), 1000, steps=3, batch=16)
+    xq = x.to(torch.bfloat16).float()
+    mine.train(); mine._b200.arena.zero_grad()
+    lo_m = mine(x)
+    F.cross_entropy(lo_m, y).backward()
+    torch.cuda.synchronize()
+    gm = torch.cat([p.grad.flatten() for p in mine.parameters()]).clone()
+    emu = _emulate_bf16_storage(copy.deepcopy(ref)).train()
+    emu.zero_grad()
+    lo_e = emu(xq)
+    F.cross_entropy(lo_e, y).backward()
+    ge = torch.cat([p.grad.flatten() for p in emu.parameters()])
+    ref.train(); ref.zero_grad()
+    lo_r = ref(xq)
+    F.cross_entropy(lo_r, y).backward()
+    gr = torch.cat([p.grad.flatten() for p in ref.parameters()])
+    print('MBv2 vs fp32: logits %.3e grad cos %.5f | emulation vs fp32: logits %.3e grad cos %.5f | vs emulation: '
+          'logits %.3e grad cos %.5f rel %.3e' % (_rel(lo_m, lo_r), _cos(gm, gr), _rel(lo_e, lo_r), _cos(ge, gr),
+                                                  _rel(lo_m, lo_e), _cos(gm, ge), _rel(gm, ge)))
+    # our drift from fp32 must be of the size of the ideal bf16-storage pipeline's own drift
+    assert _rel(lo_m, lo_r) < 2.0 * _rel(lo_e, lo_r) + 1e-3
+    assert _cos(gm, gr) > 1.0 - 2.0 * (1.0 - _cos(ge, gr)) - 1e-3
+    assert _rel(lo_m, lo_e) < 3e-2 and _cos(gm, ge) > 0.98
+    ref.eval(); mine.eval()
+    with torch.no_grad():
+        a, b = mine(x), ref(xq)
+    assert _rel(a, b) < 5e-2
