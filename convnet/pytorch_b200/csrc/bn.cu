@@ -18,7 +18,8 @@ namespace b200 {
 constexpr int kBnThreads = 256;
 constexpr int kBnMaxC = 2048;
 constexpr int kBnMaxBlocks = 1184;  // 8 per SM on 148 SMs
-constexpr int kWsFloats = 2 * kBnMaxC * 2 + 64;  // 2*C doubles + ticket counter
+constexpr int kReplicas = 16;         // accumulator copies: spreads same-address fp64 atomics over 16 lines
+constexpr int kWsFloats = kReplicas * 2 * kBnMaxC * 2 + 64;  // replicas x 2*C doubles + ticket counter
 
 struct RowMap {
   int cv, rows_per_iter;
@@ -32,9 +33,9 @@ static inline RowMap make_rowmap(int C) {
 static inline int reduce_blocks(long long M, int C, const RowMap& rm) {
   long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
   long long want = (iters + 7) / 8;          // >= 8 row-iterations per block
-  long long cap = 400000LL / (2 * C);        // bound the number of fp64 atomics (blocks * 2C)
+  long long cap = 1200000LL / (2 * C);       // bound the number of fp64 atomics (blocks * 2C)
   if (cap < sm_count()) cap = sm_count();
-  static const int per_sm = getenv("B200_BN_REDUCE_BLOCKS_PER_SM") ? atoi(getenv("B200_BN_REDUCE_BLOCKS_PER_SM")) : 3;
+  static const int per_sm = getenv("B200_BN_REDUCE_BLOCKS_PER_SM") ? atoi(getenv("B200_BN_REDUCE_BLOCKS_PER_SM")) : 6;
   if (cap > per_sm * sm_count()) cap = per_sm * sm_count();  // few, fat blocks: less same-address atomic traffic at the end
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -42,7 +43,7 @@ static inline int reduce_blocks(long long M, int C, const RowMap& rm) {
 }
 static inline int stream_blocks(long long M, const RowMap& rm) {
   long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
-  long long blocks = (iters + 7) / 8;
+  long long blocks = (iters + 15) / 16;
   if (blocks < 1) blocks = 1;
   if (blocks > 4 * kBnMaxBlocks) blocks = 4 * kBnMaxBlocks;
   return (int)blocks;
@@ -90,7 +91,7 @@ __device__ __forceinline__ bool accumulate_and_elect(float (&acc)[16], int cv, i
     const int v = c >> 3, e = c & 7;
     float s = 0.f;
     for (int r = 0; r < rows_per_iter; ++r) s += red[r * cv + v][stat * 8 + e];
-    atomicAdd(accum + o, (double)s);
+    atomicAdd(accum + (blockIdx.x % kReplicas) * 2 * C + o, (double)s);
   }
   __threadfence();
   __syncthreads();
@@ -145,9 +146,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(
     f = 1.f / (float)(nbt + 1);
   }
   for (int c = t; c < C; c += kBnThreads) {
-    const double s1 = __ldcg(accum + c), s2 = __ldcg(accum + C + c);
-    accum[c] = 0.0;
-    accum[C + c] = 0.0;
+    double s1 = 0.0, s2 = 0.0;
+    for (int rep = 0; rep < kReplicas; ++rep) {
+      s1 += __ldcg(accum + rep * 2 * C + c);
+      s2 += __ldcg(accum + rep * 2 * C + C + c);
+      accum[rep * 2 * C + c] = 0.0;
+      accum[rep * 2 * C + C + c] = 0.0;
+    }
     const double mu = s1 / (double)M;
     double var = s2 / (double)M - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -170,6 +175,44 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(
     if (num_batches_tracked != nullptr && running_mean != nullptr) *num_batches_tracked += 1;
   }
 }
+
+// finalisation of statistics accumulated elsewhere (conv epilogue): same math as the last block of bn_stats_kernel
+__global__ void __launch_bounds__(kBnThreads) bn_finalize_kernel(
+    long long M, int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+    float* running_mean, float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale,
+    float* shift, double* accum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  float f = momentum;
+  if (momentum < 0.f) {
+    const long long nbt = num_batches_tracked ? *num_batches_tracked : 0;
+    f = 1.f / (float)(nbt + 1);
+  }
+  if (c < C) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int rep = 0; rep < kReplicas; ++rep) {
+      s1 += accum[rep * 2 * C + c];
+      s2 += accum[rep * 2 * C + C + c];
+      accum[rep * 2 * C + c] = 0.0;
+      accum[rep * 2 * C + C + c] = 0.0;
+    }
+    const double mu = s1 / (double)M;
+    double var = s2 / (double)M - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float istd = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = (float)mu;
+    invstd[c] = istd;
+    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    const float sc = g * istd;
+    scale[c] = sc;
+    shift[c] = bt - (float)mu * sc;
+    if (running_mean != nullptr && running_var != nullptr) {
+      const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_mean[c] = (1.f - f) * running_mean[c] + f * (float)mu;
+      running_var[c] = (1.f - f) * running_var[c] + f * (float)unbiased;
+    }
+  }
+}
+__global__ void bn_bump_kernel(long long* nbt) { *nbt += 1; }
 
 __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv,
                                       float eps, float* scale, float* shift) {
@@ -237,7 +280,7 @@ __device__ __forceinline__ void masked_grad(const float (&dy)[8], const float (&
 }
 
 // ---- backward reduce: dbeta = sum g, dgamma = sum g * xhat ------------------------------------------
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
     long long M, int C, int cv, int rows_per_iter, int act, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, float* sums,
@@ -296,9 +339,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
   }
   if (!accumulate_and_elect(acc, cv, rows_per_iter, C, accum, ticket)) return;
   for (int c = t; c < C; c += kBnThreads) {
-    const float s1 = (float)__ldcg(accum + c), s2 = (float)__ldcg(accum + C + c);
-    accum[c] = 0.0;
-    accum[C + c] = 0.0;
+    double d1 = 0.0, d2 = 0.0;
+    for (int rep = 0; rep < kReplicas; ++rep) {
+      d1 += __ldcg(accum + rep * 2 * C + c);
+      d2 += __ldcg(accum + rep * 2 * C + C + c);
+      accum[rep * 2 * C + c] = 0.0;
+      accum[rep * 2 * C + C + c] = 0.0;
+    }
+    const float s1 = (float)d1, s2 = (float)d2;
     sums[c] = s1;
     sums[C + c] = s2;
     if (dgamma_acc) dgamma_acc[c] += s1;
@@ -309,7 +357,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
 }
 
 // ---- backward dx --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_dx_kernel(
+__global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_dx_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
     long long M, int C, int cv, int rows_per_iter, int act, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -343,29 +391,33 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_dx_kernel(
       ms.sh[i] = (beta ? be[i] : 0.f) - mu[i] * A[i];
     }
   }
-  for (long long r = row_begin + r0; r < row_end; r += 2LL * rows_per_iter) {
-    const long long rb = r + rows_per_iter;
-    const bool hb = rb < row_end;
-    float da[8], db[8], za[8], zb[8], ya[8], yb[8], ga[8], gb[8];
-    load8(dy + r * C + v * 8, da);
-    load8(z + r * C + v * 8, za);
-    if (have_y && act != B200_ACT_NONE) load8(y + r * C + v * 8, ya);
-    if (hb) {
-      load8(dy + rb * C + v * 8, db);
-      load8(z + rb * C + v * 8, zb);
-      if (have_y && act != B200_ACT_NONE) load8(y + rb * C + v * 8, yb);
+  const bool need_y = have_y && act != B200_ACT_NONE;
+  for (long long r = row_begin + r0; r < row_end; r += 4LL * rows_per_iter) {
+    uint4 rd[4], rz[4], ry[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = r + (long long)u * rows_per_iter;
+      ok[u] = rr < row_end;
+      if (ok[u]) {
+        rd[u] = *reinterpret_cast<const uint4*>(dy + rr * C + v * 8);
+        rz[u] = *reinterpret_cast<const uint4*>(z + rr * C + v * 8);
+        if (need_y) ry[u] = *reinterpret_cast<const uint4*>(y + rr * C + v * 8);
+      }
     }
-    masked_grad(da, za, ya, have_y, act, ms, ga);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) za[i] = A[i] * ga[i] + B[i] * za[i] + Cc[i];
-    store8(dz + r * C + v * 8, za);
-    if (g_out) store8(g_out + r * C + v * 8, ga);
-    if (hb) {
-      masked_grad(db, zb, yb, have_y, act, ms, gb);
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const long long rr = r + (long long)u * rows_per_iter;
+      float da[8], za[8], ya[8], ga[8];
+      unpack8(rd[u], da);
+      unpack8(rz[u], za);
+      if (need_y) unpack8(ry[u], ya);
+      masked_grad(da, za, ya, have_y, act, ms, ga);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) zb[i] = A[i] * gb[i] + B[i] * zb[i] + Cc[i];
-      store8(dz + rb * C + v * 8, zb);
-      if (g_out) store8(g_out + rb * C + v * 8, gb);
+      for (int i = 0; i < 8; ++i) za[i] = A[i] * ga[i] + B[i] * za[i] + Cc[i];
+      store8(dz + rr * C + v * 8, za);
+      if (g_out) store8(g_out + rr * C + v * 8, ga);
     }
   }
 }
@@ -376,7 +428,7 @@ static int check_c(int C, const char* who) {
   return B200_OK;
 }
 static inline double* ws_accum(float* ws) { return reinterpret_cast<double*>(ws); }
-static inline unsigned* ws_ticket(float* ws) { return reinterpret_cast<unsigned*>(ws + 2 * kBnMaxC * 2); }
+static inline unsigned* ws_ticket(float* ws) { return reinterpret_cast<unsigned*>(ws + kReplicas * 2 * kBnMaxC * 2); }
 
 }  // namespace b200
 
@@ -396,6 +448,24 @@ extern "C" int b200_bn_stats(const void* z, long long M, int C, const float* gam
       (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, gamma, beta, eps, momentum, running_mean, running_var,
       nbt, mean, invstd, scale, shift, ws_accum(workspace), ws_ticket(workspace));
   B200_CHECK_LAUNCH("bn_stats_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_finalize(long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                                float* running_mean, float* running_var, long long* nbt, float* mean, float* invstd,
+                                float* scale, float* shift, float* workspace, b200_stream_t stream_) {
+  int rc = check_c(C, "bn_finalize");
+  if (rc) return rc;
+  B200_REQUIRE(mean && invstd && scale && shift && workspace && M > 0, B200_ERR_INVALID, "bn_finalize: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // NOTE: momentum < 0 reads *nbt before the bump below (same stream => ordered)
+  bn_finalize_kernel<<<(C + kBnThreads - 1) / kBnThreads, kBnThreads, 0, stream>>>(
+      M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd, scale, shift, ws_accum(workspace));
+  B200_CHECK_LAUNCH("bn_finalize_kernel");
+  if (nbt != nullptr && running_mean != nullptr) {
+    bn_bump_kernel<<<1, 1, 0, stream>>>(nbt);
+    B200_CHECK_LAUNCH("bn_bump_kernel");
+  }
   return B200_OK;
 }
 

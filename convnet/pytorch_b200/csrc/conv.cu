@@ -22,6 +22,7 @@ constexpr int kThreads = 192;        // wgrad: TMA warp, MMA warp, 4 epilogue wa
 constexpr int kIgemmThreads = 320;   // igemm: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int kTileM = 128;
 constexpr uint32_t kTmemCols = 512;
+constexpr int kStatReplicas = 16;    // must match kReplicas of bn.cu (layout of the BN workspace accumulators)
 
 struct TapEntry {
   uint16_t off_w, off_h;  // im2col filter offsets (added to the base pixel)
@@ -46,6 +47,7 @@ struct IgemmParams {
   int act, out_fp32;
   int tma_store;         // 1: dense bf16 output staged in smem and written by TMA (tmC), residual via tmR
   int plain_a;           // 1: A is a dense [M_total, SC] matrix (1x1, stride 1, no padding): tiled TMA
+  double* stats;         // fused BN statistics accumulators [kStatReplicas][2][N_total] (BN workspace) or nullptr
   void* out;
   const void* res;
   const float* bias;
@@ -234,6 +236,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;  // the two warps of a quarter take alternate 16-column chunks
+    // fused-statistics bookkeeping: this thread owns column st_col, rows [st_row0, st_row0 + st_rows) of each tile
+    const int st_tid = threadIdx.x - 64;
+    const int st_col = st_tid % p.block_n;
+    const int st_rows = kTileM / (256 / p.block_n);
+    const int st_row0 = (st_tid / p.block_n) * st_rows;
+    int st_ntile = -1;
+    float st_s1 = 0.f, st_s2 = 0.f;
     const int IJ = p.I * p.J;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -323,6 +332,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_store_2d(&tmC, epi + b * (kTileM * 128), nbase + b * 64, m_tile * kTileM);
           bulk_commit_group();
         }
+        if (p.stats != nullptr) {
+          // Fused BN statistics: per-channel sum / sum of squares of the bf16-rounded outputs of this tile,
+          // read back from the staged tile (rows beyond M_total are exact zeros).  Accumulated in registers
+          // across the tiles of this CTA while it stays on the same channel block, then one fp64 atomic each.
+          if (st_ntile != n_tile) {
+            if (st_ntile >= 0) {
+              double* dst = p.stats + (blockIdx.x % kStatReplicas) * 2 * p.N_total + st_ntile * p.block_n + st_col;
+              atomicAdd(dst, (double)st_s1);
+              atomicAdd(dst + p.N_total, (double)st_s2);
+            }
+            st_ntile = n_tile; st_s1 = 0.f; st_s2 = 0.f;
+          }
+          const uint8_t* col = epi + (st_col >> 6) * (kTileM * 128) + (st_col & 7) * 2;
+          const int j = (st_col & 63) >> 3;
+          const int r_end = st_row0 + st_rows;
+#pragma unroll 8
+          for (int r = st_row0; r < r_end; ++r) {
+            const float vv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(col + r * 128 + ((j ^ (r & 7)) << 4)));
+            st_s1 += vv;
+            st_s2 = fmaf(vv, vv, st_s2);
+          }
+        }
         continue;
       }
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -336,6 +367,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (p.stats != nullptr && st_ntile >= 0) {
+      double* dst = p.stats + (blockIdx.x % kStatReplicas) * 2 * p.N_total + st_ntile * p.block_n + st_col;
+      atomicAdd(dst, (double)st_s1);
+      atomicAdd(dst + p.N_total, (double)st_s2);
     }
     if (p.tma_store && warp == 2 && lane == 0) bulk_wait_group0();  // smem must outlive the last TMA store
   }
@@ -585,11 +621,17 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
 static int pick_ck(int channels) { return channels <= 16 ? 16 : (channels <= 32 ? 32 : 64); }
 
 static int encode_im2col(CUtensorMap* tm, const void* base, int Nimg, int H, int W, int C, int ck, int pixels,
-                         int lower_w, int lower_h, int upper_w, int upper_h, int trav) {
+                         int lower_w, int lower_h, int upper_w, int upper_h, int trav, long long pix_stride = 0,
+                         long long row_stride = 0, long long img_stride = 0) {
   EncodeIm2colFn fn = encode_im2col_fn();
   B200_REQUIRE(fn != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeIm2col entry point unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  if (pix_stride > 0) {  // explicit (possibly overlapping) layout, in elements
+    strides[0] = (cuuint64_t)pix_stride * 2;
+    strides[1] = (cuuint64_t)row_stride * 2;
+    strides[2] = (cuuint64_t)img_stride * 2;
+  }
   int lower[2] = {lower_w, lower_h};
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)trav, (cuuint32_t)trav, 1};
@@ -654,11 +696,13 @@ static int set_smem_attr(const void* fn, int bytes) {
 // One implicit-GEMM launch.  src: [Nimg, SH, SW, SC] bf16 (im2col source); wmat: [Nout][wtaps][SC] bf16.
 struct IgemmLaunch {
   const void* src; int Nimg, SH, SW, SC;
+  long long s_pix, s_row, s_img;   // optional explicit source strides (elements), 0 = dense
   const void* wmat; int Nout, wtaps;
   int I, J, trav, lower_w, lower_h;
   int ntaps; TapEntry taps[kMaxTaps];
   void* out; int OH, OW, os, oh0, ow0, ldo;
   const void* res; const float* bias; int act, out_fp32;
+  double* stats;
 };
 
 static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
@@ -691,6 +735,11 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (p.num_stages < 2) p.num_stages = 2;
   p.OH = L.OH; p.OW = L.OW; p.os = L.os; p.oh0 = L.oh0; p.ow0 = L.ow0; p.ldo = L.ldo;
   p.act = L.act; p.out_fp32 = L.out_fp32; p.out = L.out; p.res = L.res; p.bias = L.bias;
+  p.stats = L.stats;
+  if (L.stats != nullptr)
+    B200_REQUIRE(p.tma_store && (256 % p.block_n) == 0 && L.res == nullptr && L.bias == nullptr && L.act == 0,
+                 B200_ERR_UNSUPPORTED, "conv_fprop: fused BN statistics need a dense bf16 output with K %% 64 == 0 "
+                 "(block_n=%d) and no bias/residual/activation", p.block_n);
   for (int t = 0; t < L.ntaps; ++t) p.taps[t] = L.taps[t];
 
   // bounding box of base pixels: [lower, lower + (I-1)*trav] in a source of extent SH x SW
@@ -699,12 +748,12 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   int rc;
   p.plain_a = (L.ntaps == 1 && L.trav == 1 && L.lower_w == 0 && L.lower_h == 0 && L.taps[0].off_w == 0 &&
-               L.taps[0].off_h == 0 && L.I == L.SH && L.J == L.SW) ? 1 : 0;
+               L.taps[0].off_h == 0 && L.I == L.SH && L.J == L.SW && L.s_pix == 0) ? 1 : 0;
   if (p.plain_a)
     rc = encode_tiled2(&tmA, L.src, L.SC, (long long)p.M_total, p.ck, kTileM);
   else
     rc = encode_im2col(&tmA, L.src, L.Nimg, L.SH, L.SW, L.SC, p.ck, kTileM, L.lower_w, L.lower_h, upper_w, upper_h,
-                       L.trav);
+                       L.trav, L.s_pix, L.s_row, L.s_img);
   if (rc) return rc;
   rc = encode_tiled3(&tmB, L.wmat, L.SC, L.wtaps, L.Nout, p.ck, 1, p.block_n);
   if (rc) return rc;
@@ -738,6 +787,10 @@ static int check_desc(const b200_conv_desc* d) {
                d->H, d->W, d->C, d->K, d->R, d->S, d->P, d->Q, d->stride);
   B200_REQUIRE(d->R * d->S <= kMaxTaps, B200_ERR_UNSUPPORTED, "conv: %dx%d filter exceeds %d taps", d->R, d->S,
                kMaxTaps);
+  B200_REQUIRE((d->x_pixel_stride == 0 && d->x_row_stride == 0 && d->x_image_stride == 0) ||
+                   (d->x_pixel_stride > 0 && d->x_pixel_stride % 8 == 0 && d->x_row_stride % 8 == 0 &&
+                    d->x_image_stride % 8 == 0 && d->x_row_stride > 0 && d->x_image_stride > 0),
+               B200_ERR_INVALID, "conv: x strides must all be 0 (dense) or positive multiples of 8 elements");
   return B200_OK;
 }
 
@@ -754,6 +807,7 @@ extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const voi
   IgemmLaunch L;
   memset(&L, 0, sizeof(L));
   L.src = x; L.Nimg = d->N; L.SH = d->H; L.SW = d->W; L.SC = d->C;
+  L.s_pix = d->x_pixel_stride; L.s_row = d->x_row_stride; L.s_img = d->x_image_stride;
   L.wmat = w; L.Nout = d->K; L.wtaps = d->R * d->S;
   L.I = d->P; L.J = d->Q; L.trav = d->stride; L.lower_w = -d->pad_w; L.lower_h = -d->pad_h;
   L.ntaps = d->R * d->S;
@@ -767,6 +821,7 @@ extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const voi
   L.bias = ep ? ep->bias : nullptr;
   L.act = ep ? ep->act : 0;
   L.out_fp32 = ep ? ep->out_fp32 : 0;
+  L.stats = (ep && ep->bn_stats_workspace) ? reinterpret_cast<double*>(ep->bn_stats_workspace) : nullptr;
   return launch_igemm(L, (cudaStream_t)stream);
 }
 
@@ -901,12 +956,12 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   const int upper_w = p.lower_w + (d->Q - 1) * d->stride + 1 - d->W;
   const int upper_h = p.lower_h + (d->P - 1) * d->stride + 1 - d->H;
   p.plain_x = (d->R == 1 && d->S == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && d->P == d->H &&
-               d->Q == d->W) ? 1 : 0;
+               d->Q == d->W && d->x_pixel_stride == 0) ? 1 : 0;
   if (p.plain_x)
     rc = encode_tiled2(&tmX, x, d->C, (long long)p.M_total, p.ckB, p.bk);
   else
     rc = encode_im2col(&tmX, x, d->N, d->H, d->W, d->C, p.ckB, p.bk, p.lower_w, p.lower_h, upper_w, upper_h,
-                       d->stride);
+                       d->stride, d->x_pixel_stride, d->x_row_stride, d->x_image_stride);
   if (rc) return rc;
   const int smem_bytes = p.num_stages * (int)p.stage_bytes + 1024;
   rc = set_smem_attr((const void*)conv_wgrad_kernel, smem_bytes);

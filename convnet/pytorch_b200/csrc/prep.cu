@@ -11,15 +11,17 @@ namespace b200 {
 __global__ void __launch_bounds__(256) input_prep_kernel(const float* __restrict__ x, int N, int C, int H, int W,
                                                          int Cpad, int mode, __nv_bfloat16* __restrict__ out) {
   // one thread per output pixel; Cpad is a multiple of 8
-  const int OH = mode == 1 ? H / 2 : H, OW = mode == 1 ? W / 2 : W;
+  const int brd = mode == 2 ? 2 : 0;                       // low border of the padded space-to-depth layout
+  const int OH = mode == 0 ? H : H / 2 + (mode == 2 ? 3 : 0), OW = mode == 0 ? W : W / 2 + (mode == 2 ? 3 : 0);
   const long long total = (long long)N * OH * OW;
   const long long plane = (long long)H * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx % OW);
-    const int i = (int)((idx / OW) % OH);
+    const int j = (int)(idx % OW) - brd;
+    const int i = (int)((idx / OW) % OH) - brd;
     const int n = (int)(idx / ((long long)OW * OH));
     __nv_bfloat16* o = out + idx * Cpad;
+    const bool inside = mode != 2 || (i >= 0 && j >= 0 && i < H / 2 && j < W / 2);
     const float* xi = x + (long long)n * C * plane;
     for (int c0 = 0; c0 < Cpad; c0 += 8) {
       float f[8];
@@ -31,7 +33,7 @@ __global__ void __launch_bounds__(256) input_prep_kernel(const float* __restrict
           if (ch < C) val = __ldg(xi + (long long)ch * plane + (long long)i * W + j);
         } else {
           const int sub = ch / C, c = ch - sub * C;  // sub = dy*2+dx
-          if (sub < 4) {
+          if (sub < 4 && inside) {
             const int dy = sub >> 1, dx = sub & 1;
             val = __ldg(xi + (long long)c * plane + (long long)(2 * i + dy) * W + (2 * j + dx));
           }
@@ -130,13 +132,13 @@ extern "C" int b200_input_prep(const float* x, int N, int C, int H, int W, int C
   B200_REQUIRE(Cpad % 8 == 0, B200_ERR_UNSUPPORTED, "input_prep: Cpad=%d must be a multiple of 8", Cpad);
   if (mode == 0) {
     B200_REQUIRE(Cpad >= C, B200_ERR_INVALID, "input_prep: Cpad < C");
-  } else if (mode == 1) {
+  } else if (mode == 1 || mode == 2) {
     B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cpad >= 4 * C, B200_ERR_UNSUPPORTED,
                  "input_prep: space-to-depth needs even H,W and Cpad >= 4C");
   } else {
     B200_REQUIRE(false, B200_ERR_INVALID, "input_prep: unknown mode %d", mode);
   }
-  const long long total = (long long)N * (mode == 1 ? (H / 2) * (W / 2) : H * W);
+  const long long total = (long long)N * (mode == 0 ? (long long)H * W : (long long)(H / 2 + (mode == 2 ? 3 : 0)) * (W / 2 + (mode == 2 ? 3 : 0)));
   input_prep_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(x, N, C, H, W, Cpad, mode,
                                                                           (__nv_bfloat16*)out);
   B200_CHECK_LAUNCH("input_prep_kernel");

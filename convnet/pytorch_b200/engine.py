@@ -14,6 +14,8 @@ attribute names) and
 Nothing here computes on the CPU or through cuDNN/cuBLAS: a missing library or an unsupported layer
 raises ``B200Error``.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -21,6 +23,8 @@ from . import ops
 from .lib import B200Error, ACT_NONE, ACT_RELU, ACT_RELU6
 
 _ALIGN = 64  # elements; keeps every slot 128B-aligned in the bf16 shadow (TMA needs 16B)
+WIDE_STEM = os.environ.get('B200_WIDE_STEM', '1') != '0'  # overlapping-pixel TMA view for the ImageNet stem
+FUSE_BN_STATS = os.environ.get('B200_FUSE_BN_STATS', '1') != '0'  # BN statistics in the conv epilogue
 
 
 def _round_up(n, m):
@@ -196,22 +200,34 @@ class Runtime(object):
         u = _Unit()
         u.conv, u.bn, u.act, u.x = conv, bn, act, x
         u.desc = conv.desc(N, H, W)
-        u.z = ops.conv_fprop(x, conv.w16, u.desc)
-        self._bn_coeffs(u, training)
+        self._conv_and_coeffs(u, x, conv.w16, training)
         if other is not None:
             u.y = ops.bn_apply(u.z, u.scale, u.shift, act, z2=other.z, scale2=other.scale, shift2=other.shift)
         else:
             u.y = ops.bn_apply(u.z, u.scale, u.shift, act, residual=residual)
         return u
 
-    def _bn_coeffs(self, u, training):
+    def _conv_and_coeffs(self, u, x, w16, training):
+        """z = conv(x) and the BN coefficients; in training the statistics are accumulated by the conv epilogue
+        itself whenever the output width allows it (saves one full read of z)."""
+        if training and FUSE_BN_STATS and ops.can_fuse_bn_stats(u.desc.K):
+            u.z = ops.conv_fprop(x, w16, u.desc, bn_stats_ws=self._ws)
+            self._bn_coeffs(u, training, fused=True)
+        else:
+            u.z = ops.conv_fprop(x, w16, u.desc)
+            self._bn_coeffs(u, training)
+
+    def _bn_coeffs(self, u, training, fused=False):
         bn = u.bn
         C = bn.C
         buf = self._coeffs(6 * C)
         u.mean, u.invstd, u.scale, u.shift, u.sums = buf[0:C], buf[C:2 * C], buf[2 * C:3 * C], buf[3 * C:4 * C], \
             buf[4 * C:6 * C]
         m = bn.mod
-        if training:
+        if training and fused:
+            ops.bn_finalize(u.z.numel() // C, C, bn.gamma, bn.beta, m.eps, m.momentum, m.running_mean, m.running_var,
+                            m.num_batches_tracked, u.mean, u.invstd, u.scale, u.shift, self._ws)
+        elif training:
             ops.bn_stats(u.z, bn.gamma, bn.beta, m.eps, m.momentum, m.running_mean, m.running_var,
                          m.num_batches_tracked, u.mean, u.invstd, u.scale, u.shift, self._ws)
         else:
@@ -223,8 +239,7 @@ class Runtime(object):
         u = _Unit()
         u.conv, u.bn, u.act, u.x = conv, bn, ACT_NONE, x
         u.desc = conv.desc(N, H, W)
-        u.z = ops.conv_fprop(x, conv.w16, u.desc)
-        self._bn_coeffs(u, training)
+        self._conv_and_coeffs(u, x, conv.w16, training)
         u.y = None
         return u
 
@@ -375,10 +390,19 @@ class ResNetRuntime(Runtime):
         x = x.float().contiguous()
         st = {}
         if self.imagenet_stem:
-            xs = ops.input_prep(x, 16, s2d=True)                       # [N, H/2, W/2, 16]
             ws = torch.empty((K, 16, 16), device=self.device, dtype=torch.bfloat16)
             ops.stem_weight_to_s2d(self.stem_w32, K, Cin, 16, ws)
-            desc = ops.make_desc(N, H // 2, W // 2, 16, K, 4, 4, 1, 2, P=H // 2, Q=W // 2)
+            Hs, Ws = H // 2, W // 2
+            if WIDE_STEM:
+                # 7x7/s2 -> space-to-depth 4x4/s1 on 16 channels -> 4x1 on "wide pixels": 4 neighbouring 32-byte
+                # pixels of the zero-bordered tensor are read as ONE 64-channel (128 B) pixel, so every tap row is a
+                # full 128B-swizzle TMA tile (4 loads per tile instead of 16 quarter-width ones).
+                xs = ops.input_prep(x, 16, s2d=True, border=True)      # [N, Hs+3, Ws+3, 16], data at (+2,+2)
+                desc = ops.make_desc(N, Hs + 3, Ws, 64, K, 4, 1, 1, 0, P=Hs, Q=Ws,
+                                     x_strides=(16, (Ws + 3) * 16, (Hs + 3) * (Ws + 3) * 16))
+            else:
+                xs = ops.input_prep(x, 16, s2d=True)                   # [N, H/2, W/2, 16]
+                desc = ops.make_desc(N, Hs, Ws, 16, K, 4, 4, 1, 2, P=Hs, Q=Ws)
         else:
             xs = ops.input_prep(x, 16, s2d=False)
             ws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.bfloat16)
@@ -386,8 +410,7 @@ class ResNetRuntime(Runtime):
             desc = ops.make_desc(N, H, W, 16, K, 3, 3, 1, 1)
         u = _Unit()
         u.conv, u.bn, u.act, u.x, u.desc = None, self.stem_bn, ACT_RELU, xs, desc
-        u.z = ops.conv_fprop(xs, ws, desc)
-        self._bn_coeffs(u, training)
+        self._conv_and_coeffs(u, xs, ws, training)
         u.y = ops.bn_apply(u.z, u.scale, u.shift, ACT_RELU)
         st['unit'] = u
         out = u.y

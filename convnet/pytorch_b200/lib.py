@@ -20,12 +20,13 @@ class B200Error(RuntimeError):
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
-                ("N", "H", "W", "C", "K", "R", "S", "stride", "pad_h", "pad_w", "P", "Q")]
+                ("N", "H", "W", "C", "K", "R", "S", "stride", "pad_h", "pad_w", "P", "Q",
+                 "x_pixel_stride", "x_row_stride", "x_image_stride")]
 
 
 class Epilogue(ctypes.Structure):
     _fields_ = [("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
-                ("act", ctypes.c_int), ("out_fp32", ctypes.c_int)]
+                ("act", ctypes.c_int), ("out_fp32", ctypes.c_int), ("bn_stats_workspace", ctypes.c_void_p)]
 
 
 _vp, _i, _ll, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
@@ -43,6 +44,7 @@ SIGNATURES = {
     "b200_dwconv_wgrad": [_dp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_bn_workspace_floats": [_i],
     "b200_bn_stats": [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200_bn_finalize": [_ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_bn_eval_coeffs": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp],
     "b200_bn_apply": [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "b200_bn_bwd_reduce": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -82,21 +82,29 @@ def out_size(h, r, stride, pad_lo, pad_hi=None):
     return (h + pad_lo + pad_hi - r) // stride + 1
 
 
-def make_desc(N, H, W, C, K, R, S, stride, pad, P=None, Q=None):
+def make_desc(N, H, W, C, K, R, S, stride, pad, P=None, Q=None, x_strides=(0, 0, 0)):
     pad_h, pad_w = (pad, pad) if isinstance(pad, int) else pad
     P = out_size(H, R, stride, pad_h) if P is None else P
     Q = out_size(W, S, stride, pad_w) if Q is None else Q
-    return ConvDesc(N, H, W, C, K, R, S, stride, pad_h, pad_w, P, Q)
+    return ConvDesc(N, H, W, C, K, R, S, stride, pad_h, pad_w, P, Q, *x_strides)
 
 
 # ------------------------------------------------------------------------------------ convolution
-def conv_fprop(x, w, desc, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32=False):
-    """x [N,H,W,C] bf16, w [K,R*S,C] bf16 -> y [N,P,Q,K] (bf16, or fp32 if out_fp32)."""
+def can_fuse_bn_stats(K):
+    """b200_conv_fprop can accumulate BN statistics in its epilogue when the output tile is 64/128/256 wide."""
+    n_tiles = (K + 255) // 256
+    block_n = ((K + n_tiles - 1) // n_tiles + 15) // 16 * 16
+    return K % 64 == 0 and K % block_n == 0 and 256 % block_n == 0
+
+
+def conv_fprop(x, w, desc, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32=False, bn_stats_ws=None):
+    """x [N,H,W,C] bf16, w [K,R*S,C] bf16 -> y [N,P,Q,K] (bf16, or fp32 if out_fp32).
+    bn_stats_ws: BN workspace into which the epilogue accumulates per-channel sum / sum^2 (finish: bn_finalize)."""
     _chk(x, bf16, "x"); _chk(w, bf16, "w"); _chk(bias, torch.float32, "bias"); _chk(residual, bf16, "residual")
     if out is None:
         out = torch.empty((desc.N, desc.P, desc.Q, desc.K), device=x.device,
                           dtype=torch.float32 if out_fp32 else bf16)
-    ep = Epilogue(_l.ptr(bias), _l.ptr(residual), int(act), int(bool(out_fp32)))
+    ep = Epilogue(_l.ptr(bias), _l.ptr(residual), int(act), int(bool(out_fp32)), _l.ptr(bn_stats_ws))
     with _T('conv_fprop', _conv_flops(desc), 0):
         _l.check(_l.load().b200_conv_fprop(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), out.data_ptr(),
                                            ctypes.byref(ep), _stream()), "b200_conv_fprop")
@@ -176,6 +184,15 @@ def bn_stats(z, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean
                                          _l.ptr(running_mean), _l.ptr(running_var), _l.ptr(nbt), mean.data_ptr(),
                                          invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), workspace.data_ptr(),
                                          _stream()), "b200_bn_stats")
+
+
+def bn_finalize(M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd, scale, shift, workspace):
+    mom = -1.0 if momentum is None else float(momentum)
+    with _T('bn_stats', 0, 0):
+        _l.check(_l.load().b200_bn_finalize(int(M), int(C), _l.ptr(gamma), _l.ptr(beta), float(eps), mom,
+                                            _l.ptr(running_mean), _l.ptr(running_var), _l.ptr(nbt), mean.data_ptr(),
+                                            invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                            workspace.data_ptr(), _stream()), "b200_bn_finalize")
 
 
 def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, scale, shift):
@@ -260,14 +277,18 @@ def avgpool_bwd(dy, in_shape):
 
 
 # ------------------------------------------------------------------------------------ layout / casts
-def input_prep(x_nchw, cpad, s2d=False):
-    """NCHW fp32 -> NHWC bf16 (channels zero-padded to cpad) or its 2x2 space-to-depth form."""
+def input_prep(x_nchw, cpad, s2d=False, border=False):
+    """NCHW fp32 -> NHWC bf16 (channels zero-padded to cpad) or its 2x2 space-to-depth form (optionally with
+    the physical zero border of mode 2: +2 low / +1 high in H and W)."""
     _chk(x_nchw, torch.float32, "x")
     N, C, H, W = x_nchw.shape
-    shape = (N, H // 2, W // 2, cpad) if s2d else (N, H, W, cpad)
+    if s2d and border:
+        shape = (N, H // 2 + 3, W // 2 + 3, cpad)
+    else:
+        shape = (N, H // 2, W // 2, cpad) if s2d else (N, H, W, cpad)
     out = torch.empty(shape, device=x_nchw.device, dtype=bf16)
     with _T('input_prep', 0, 4 * x_nchw.numel() + 2 * out.numel()):
-        _l.check(_l.load().b200_input_prep(x_nchw.data_ptr(), N, C, H, W, cpad, 1 if s2d else 0, out.data_ptr(),
+        _l.check(_l.load().b200_input_prep(x_nchw.data_ptr(), N, C, H, W, cpad, (2 if border else 1) if s2d else 0, out.data_ptr(),
                                            _stream()), "b200_input_prep")
     return out
 

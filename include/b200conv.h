@@ -43,6 +43,10 @@ typedef struct {
   int stride;
   int pad_h, pad_w;
   int P, Q;
+  /* optional layout of x in ELEMENTS (0 = dense NHWC: C, W*C, H*W*C).  A pixel stride smaller than C makes
+   * consecutive "pixels" overlap: the space-to-depth ImageNet stem reads 4 neighbouring 16-channel pixels as
+   * one 64-channel pixel this way (only x is affected; y / dy are always dense). */
+  int x_pixel_stride, x_row_stride, x_image_stride;
 } b200_conv_desc;
 
 typedef struct {
@@ -50,6 +54,9 @@ typedef struct {
   const void* residual;  /* bf16, same shape as the output, added before act; or NULL */
   int act;               /* B200_ACT_*                                         */
   int out_fp32;          /* 1: output is fp32 (logits), 0: bf16                */
+  float* bn_stats_workspace; /* non-NULL: also accumulate per-channel sum / sum^2 of the (bf16) output into this BN
+                              * workspace (see b200_bn_workspace_floats); finish with b200_bn_finalize.  Needs a
+                              * dense bf16 output, K % 64 == 0, no bias/residual/act; else B200_ERR_UNSUPPORTED */
 } b200_epilogue;
 
 const char* b200_last_error(void);
@@ -92,6 +99,10 @@ int b200_bn_stats(const void* z, long long M, int C, const float* gamma, const f
                   float eps, float momentum, float* running_mean, float* running_var,
                   long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
                   float* workspace, b200_stream_t stream);
+/* second half of b200_bn_stats for statistics accumulated by b200_conv_fprop (bn_stats_workspace) */
+int b200_bn_finalize(long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, long long* num_batches_tracked, float* mean,
+                     float* invstd, float* scale, float* shift, float* workspace, b200_stream_t stream);
 /* eval mode: scale/shift from running statistics */
 int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float* scale, float* shift, b200_stream_t stream);
@@ -123,7 +134,9 @@ int b200_avgpool_bwd(const void* dy, int N, int HW, int C, void* dx, b200_stream
  * replaces inputs.to(device, dtype) (trainer.py:116-117) + the NCHW->NHWC relayout.
  * mode 0: NCHW fp32 -> NHWC bf16 with channels zero-padded to Cpad.
  * mode 1: space-to-depth by 2 for the 7x7/s2 ImageNet stem: out[N,H/2,W/2,Cpad], channel =
- *         (dy*2+dx)*C + c, zero-padded to Cpad (H, W even). */
+ *         (dy*2+dx)*C + c, zero-padded to Cpad (H, W even).
+ * mode 2: mode 1 with a physical zero border: out[N, H/2+3, W/2+3, Cpad], data at (+2,+2) -- the 4x4/s1
+ *         stem conv (pad 2 low, 1 high) then needs no out-of-bounds handling and can read "wide pixels". */
 int b200_input_prep(const float* x_nchw, int N, int C, int H, int W, int Cpad, int mode, void* out, b200_stream_t stream);
 /* bf16 [K][T][C] -> bf16 [C][T][K] (dgrad weight layout), multi-tensor: n tensors described by
  * device arrays. */

@@ -268,3 +268,64 @@ def test_depthwise(N, H, C, stride):
     ws = torch.empty(592 * 9 * C).cuda()
     ops.dwconv_wgrad(x, dy, desc, dw, ws)
     assert rel(dw, gw.reshape(C, 9).t()) < 1e-5
+
+
+def test_wide_pixel_stem_matches_7x7_conv():
+    """bordered space-to-depth input read as overlapping 64-channel 'wide pixels' (4x1 conv) == 7x7/s2/p3 conv,
+    forward and weight gradient (the ImageNet stem path of engine.ResNetRuntime)."""
+    ops = _ops()
+    N, H, W, K = 3, 64, 96, 32
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, 3, H, W, generator=g).cuda()
+    w = (torch.randn(K, 7, 7, 3, generator=g) / 12).cuda()      # KRSC master layout
+    ws = torch.empty(K, 16, 16, device='cuda', dtype=bf16)
+    ops.stem_weight_to_s2d(w, K, 3, 16, ws)
+    Hs, Ws = H // 2, W // 2
+    xs = ops.input_prep(x, 16, s2d=True, border=True)
+    assert xs.shape == (N, Hs + 3, Ws + 3, 16)
+    assert float(xs[:, :2].float().abs().sum()) == 0 and float(xs[:, :, -1].float().abs().sum()) == 0
+    desc = ops.make_desc(N, Hs + 3, Ws, 64, K, 4, 1, 1, 0, P=Hs, Q=Ws,
+                         x_strides=(16, (Ws + 3) * 16, (Hs + 3) * (Ws + 3) * 16))
+    y = ops.conv_fprop(xs, ws, desc)
+    xr = x.to(bf16).double().requires_grad_(False)
+    wr = w.to(bf16).double().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=2, padding=3)
+    assert close_bf16(y.permute(0, 3, 1, 2), yr.detach())
+    dy = torch.randn(N, Hs, Ws, K, generator=g).cuda().to(bf16)
+    gw, = torch.autograd.grad(yr, wr, dy.double().permute(0, 3, 1, 2))
+    dws = torch.zeros(K, 16, 16, device='cuda')
+    ops.conv_wgrad(xs, dy, desc, dws)
+    dw = torch.zeros(K, 7, 7, 3, device='cuda')
+    ops.stem_wgrad_from_s2d(dws, K, 3, 16, dw)
+    assert rel(dw, gw.permute(0, 2, 3, 1)) < 1e-4
+
+
+@pytest.mark.parametrize("N,H,C,K,R", [(4, 28, 64, 64, 3), (8, 14, 128, 256, 1), (3, 9, 64, 512, 1), (2, 56, 64, 128, 1)])
+def test_fused_bn_statistics_in_conv_epilogue(N, H, C, K, R):
+    """conv_fprop(bn_stats_ws=...) + bn_finalize == conv_fprop followed by bn_stats on its output."""
+    ops = _ops()
+    assert ops.can_fuse_bn_stats(K)
+    g = torch.Generator().manual_seed(K + C)
+    x = torch.randn(N, H, H, C, generator=g).cuda().to(bf16)
+    w = (torch.randn(K, R * R, C, generator=g) / (R * R * C) ** 0.5).cuda().to(bf16)
+    desc = ops.make_desc(N, H, H, C, K, R, R, 1, R // 2)
+    gamma, beta = (torch.rand(K, generator=g) + 0.5).cuda(), torch.randn(K, generator=g).cuda()
+    ws = torch.zeros(ops.bn_workspace_floats(K)).cuda()
+    outs = []
+    for fused in (False, True):
+        rm, rv = torch.zeros(K).cuda(), torch.ones(K).cuda()
+        nbt = torch.zeros((), dtype=torch.int64).cuda()
+        bufs = [torch.empty(K).cuda() for _ in range(4)]
+        if fused:
+            z = ops.conv_fprop(x, w, desc, bn_stats_ws=ws)
+            ops.bn_finalize(z.numel() // K, K, gamma, beta, 1e-5, 0.1, rm, rv, nbt, *bufs, ws)
+        else:
+            z = ops.conv_fprop(x, w, desc)
+            ops.bn_stats(z, gamma, beta, 1e-5, 0.1, rm, rv, nbt, *bufs, ws)
+        torch.cuda.synchronize()
+        outs.append((z, rm, rv, int(nbt), bufs))
+    (z0, rm0, rv0, n0, b0), (z1, rm1, rv1, n1, b1) = outs
+    assert torch.equal(z0, z1) and n0 == n1 == 1
+    for a, b in zip(b0 + [rm0, rv0], b1 + [rm1, rv1]):
+        assert rel(b, a) < 1e-5
+    assert float(ws.abs().sum()) == 0.0      # the workspace is left zeroed

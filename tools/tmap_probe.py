@@ -1,5 +1,7 @@
 """Does cuTensorMapEncode{Tiled,Im2col} accept OVERLAPPING rows (stride of dim1 smaller than the extent of dim0)?"""
 import ctypes
+import torch
+torch.zeros(1, device='cuda')   # creates and binds the primary context
 cu = ctypes.CDLL('libcuda.so.1')
 print('cuInit', cu.cuInit(0))
 tm = (ctypes.c_uint64 * 16)()
