@@ -38,6 +38,9 @@ def parse():
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     p.add_argument('--batch', type=int, default=256, help='per-GPU batch')
     p.add_argument('--depth', type=int, default=50)
+    p.add_argument('--model', default='resnet', choices=['resnet', 'resnext', 'mobilenet_v2'],
+                   help='extra configurations (BASELINE configs[2..4]); the contract line is the default resnet-50')
+    p.add_argument('--size', type=int, default=IMG, help='input resolution (Mix&Match sweep: 128..288)')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--cpu-batch', type=int, default=32)
@@ -172,14 +175,17 @@ def main():
 
     B = args.batch
     torch.manual_seed(123)
-    model = models.resnet(dataset='imagenet', depth=args.depth)
+    if args.model == 'mobilenet_v2':
+        model = models.mobilenet_v2(dataset='imagenet')
+    else:
+        model = getattr(models, args.model)(dataset='imagenet', depth=args.depth)
     convert_b200(model, dev)
     criterion = CrossEntropyLoss().to(dev)
     optimizer = OptimRegime(model, model.regime)
     trainer = Trainer(model, criterion, optimizer, device_ids=[local], device=str(dev), dtype=torch.float,
                       distributed=distributed, local_rank=local, print_freq=10 ** 9)
     g = torch.Generator().manual_seed(rank)            # per-rank data (DistributedSampler analogue)
-    x_host = torch.randn(B, 3, IMG, IMG, generator=g).pin_memory()
+    x_host = torch.randn(B, 3, args.size, args.size, generator=g).pin_memory()
     y_host = torch.randint(0, CLASSES, (B,), generator=g).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     model.train()
@@ -284,25 +290,29 @@ def main():
         roof['classes'] = {n: {'ms': round(c['ms'], 3), 'calls': c['calls']} for n, c in sorted(classes.items())}
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    default_cfg = args.model == 'resnet' and args.depth == 50 and args.size == IMG
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and default_cfg:
         cb = cpu_reference(args.cpu_batch, 3, 1, args.depth)
         cpu_base = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
 
     if rank == 0:
         ips = world * B * args.steps / (ms * 1e-3)
-        line = {'metric': 'ResNet-50 images/sec (training step, synthetic 224x224)', 'value': ips,
+        name = {'resnet': 'ResNet-%d', 'resnext': 'ResNeXt-%d 32x4d', 'mobilenet_v2': 'MobileNet-v2'}[args.model]
+        name = name % args.depth if '%d' in name else name
+        line = {'metric': '%s images/sec (training step, synthetic %dx%d)' % (name, args.size, args.size), 'value': ips,
                 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16', 'data': 'synthetic',
-                'config': {'workload': 'ResNet-%d bf16 (fp32 master weights), synthetic ImageNet 224x224, batch %d/GPU, '
-                                       'SGD momentum 0.9 + WeightDecay 1e-4 (BASELINE.json configs[1])'
-                                       % (args.depth, B),
+                'config': {'workload': '%s bf16 (fp32 master weights), synthetic ImageNet %dx%d, batch %d/GPU, '
+                                       'SGD momentum 0.9 + WeightDecay 1e-4%s'
+                                       % (name, args.size, args.size, B,
+                                          ' (BASELINE.json configs[1])' if default_cfg else ''),
                            'global_batch': world * B, 'parallelism': 'dp%d' % world,
                            'l2_policy': 'per-step working set (activations ~10 GB) >> 126 MB L2; no explicit flush'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu_base,
                 'final_loss': final_loss,
                 'conv_tensor_pipe_frac': (world * B * args.steps * TRAIN_CONV_GFLOP_PER_IMG / (ms * 1e-3) / 1e3
-                                          / (world * peaks()['tflops']))}
+                                          / (world * peaks()['tflops'])) if default_cfg else None}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()

@@ -176,3 +176,59 @@ extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, b
   B200_CHECK_LAUNCH("cast_f32_bf16_kernel");
   return B200_OK;
 }
+
+// ---- grouped convolution support (ResNeXt): block-diagonal dense expansion of the weights ----------------------
+// w_g fp32 [K][T][C/g]  ->  dense bf16 [K][T][C] with zeros outside the group of output channel k;
+// the dense tcgen05 kernels then serve the grouped layer (extra MACs on zeros, no new data path), and the
+// gradient is extracted from the dense wgrad result.  (reference: nn.Conv2d(groups=32), models/resnext.py:10-16)
+namespace b200 {
+__global__ void __launch_bounds__(256) group_expand_kernel(const float* __restrict__ wg, int K, int T, int C, int groups,
+                                                           __nv_bfloat16* __restrict__ out) {
+  const int cg = C / groups, kg = K / groups;
+  const long long total = (long long)K * T * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int t = (int)((idx / C) % T);
+    const int k = (int)(idx / ((long long)C * T));
+    const int grp = k / kg;
+    float v = 0.f;
+    if (c / cg == grp) v = wg[((long long)k * T + t) * cg + (c - grp * cg)];
+    out[idx] = __float2bfloat16(v);
+  }
+}
+__global__ void __launch_bounds__(256) group_extract_kernel(const float* __restrict__ dw_dense, int K, int T, int C,
+                                                            int groups, float* __restrict__ dwg) {
+  const int cg = C / groups, kg = K / groups;
+  const long long total = (long long)K * T * cg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cl = (int)(idx % cg);
+    const int t = (int)((idx / cg) % T);
+    const int k = (int)(idx / ((long long)cg * T));
+    dwg[idx] += dw_dense[((long long)k * T + t) * C + (k / kg) * cg + cl];
+  }
+}
+}  // namespace b200
+
+extern "C" int b200_group_weight_expand(const float* w_grouped, int K, int T, int C, int groups, void* w_dense_bf16,
+                                        b200_stream_t stream) {
+  B200_REQUIRE(w_grouped && w_dense_bf16 && K > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && K % groups == 0,
+               B200_ERR_INVALID, "group_weight_expand: bad argument");
+  const long long total = (long long)K * T * C;
+  b200::group_expand_kernel<<<b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_grouped, K, T, C, groups, (__nv_bfloat16*)w_dense_bf16);
+  B200_CHECK_LAUNCH("group_expand_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_group_wgrad_extract(const float* dw_dense, int K, int T, int C, int groups, float* dw_grouped,
+                                        b200_stream_t stream) {
+  B200_REQUIRE(dw_dense && dw_grouped && K > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && K % groups == 0,
+               B200_ERR_INVALID, "group_wgrad_extract: bad argument");
+  const long long total = (long long)K * T * (C / groups);
+  b200::group_extract_kernel<<<b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_dense, K, T, C, groups,
+                                                                                        dw_grouped);
+  B200_CHECK_LAUNCH("group_extract_kernel");
+  return B200_OK;
+}

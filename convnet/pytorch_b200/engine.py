@@ -54,10 +54,9 @@ class Arena(object):
                 s.alloc = s.numel
                 if isinstance(mod, nn.Conv2d) and p_name == 'weight':
                     depthwise = mod.groups > 1 and mod.groups == mod.in_channels and mod.in_channels == mod.out_channels
-                    if mod.groups > 1 and not depthwise:
-                        raise B200Error('grouped convolution (groups=%d) in %s is not served by the B200 kernels yet'
-                                        % (mod.groups, s.name))
-                    s.kind = 'dw' if depthwise else 'conv'
+                    if mod.groups > 1 and not depthwise and (mod.in_channels % mod.groups or mod.out_channels % mod.groups):
+                        raise B200Error('grouped convolution %s: channels not divisible by groups' % s.name)
+                    s.kind = 'dw' if depthwise else 'conv'   # grouped weights [K, C/g, R, S] use the same KRSC view
                     s.group = 1 if depthwise else 0
                 elif isinstance(mod, nn.Linear) and p_name == 'weight':
                     s.kind, s.group = 'fc', 0
@@ -144,12 +143,20 @@ class _Conv(object):
         if mod.stride[0] != mod.stride[1] or mod.padding[0] != mod.padding[1] or mod.dilation != (1, 1) \
                 or mod.bias is not None:
             raise B200Error('conv %s: only square stride/padding, dilation 1 and bias=False are supported' % s.name)
+        self.groups = mod.groups if s.kind == 'conv' else 1
         self.w16 = arena.kernel_view(arena.p16, s)
         self.w32 = arena.kernel_view(arena.p32, s)
         self.g32 = arena.kernel_view(arena.g32, s)
 
     def desc(self, N, H, W):
         return ops.make_desc(N, H, W, self.C, self.K, self.R, self.S, self.stride, self.pad)
+
+    def kernel_weights(self):
+        """bf16 [K, R*S, C] operand of the dense kernels: the arena shadow, or for a grouped convolution the
+        block-diagonal expansion of the fp32 master (zeros outside each output channel's group)."""
+        if self.groups == 1:
+            return self.w16
+        return ops.group_weight_expand(self.w32, self.K, self.R * self.S, self.C, self.groups)
 
 
 class _BN(object):
@@ -167,7 +174,7 @@ class _BN(object):
 
 class _Unit(object):
     """saved state of one conv+BN unit for backward."""
-    __slots__ = ('x', 'z', 'y', 'desc', 'mean', 'invstd', 'scale', 'shift', 'sums', 'conv', 'bn', 'act')
+    __slots__ = ('x', 'z', 'y', 'w', 'desc', 'mean', 'invstd', 'scale', 'shift', 'sums', 'conv', 'bn', 'act')
 
 
 class Runtime(object):
@@ -200,7 +207,8 @@ class Runtime(object):
         u = _Unit()
         u.conv, u.bn, u.act, u.x = conv, bn, act, x
         u.desc = conv.desc(N, H, W)
-        self._conv_and_coeffs(u, x, conv.w16, training)
+        u.w = conv.kernel_weights()
+        self._conv_and_coeffs(u, x, u.w, training)
         if other is not None:
             u.y = ops.bn_apply(u.z, u.scale, u.shift, act, z2=other.z, scale2=other.scale, shift2=other.shift)
         else:
@@ -239,7 +247,8 @@ class Runtime(object):
         u = _Unit()
         u.conv, u.bn, u.act, u.x = conv, bn, ACT_NONE, x
         u.desc = conv.desc(N, H, W)
-        self._conv_and_coeffs(u, x, conv.w16, training)
+        u.w = conv.kernel_weights()
+        self._conv_and_coeffs(u, x, u.w, training)
         u.y = None
         return u
 
@@ -255,10 +264,17 @@ class Runtime(object):
 
     def _conv_bwd(self, u, dz, need_dx=True, residual=None):
         """wgrad into the gradient arena and (optionally) dgrad."""
-        ops.conv_wgrad(u.x, dz, u.desc, u.conv.g32)
+        conv = u.conv
+        if conv.groups == 1:
+            ops.conv_wgrad(u.x, dz, u.desc, conv.g32)
+        else:  # dense wgrad into a scratch, then keep the diagonal (group) blocks
+            T = conv.R * conv.S
+            dense = torch.zeros((conv.K, T, conv.C), device=self.device, dtype=torch.float32)
+            ops.conv_wgrad(u.x, dz, u.desc, dense)
+            ops.group_wgrad_extract(dense, conv.K, T, conv.C, conv.groups, conv.g32)
         if not need_dx:
             return None
-        wt = ops.weight_transpose(u.conv.w16)
+        wt = ops.weight_transpose(u.w)
         return ops.conv_dgrad(dz, wt, u.desc, residual=residual)
 
     # ---- classifier head: global average pool -> (dropout) -> linear as a 1x1 conv on a 1x1 map ----------
@@ -534,8 +550,13 @@ class MobileNetRuntime(Runtime):
         u = _Unit()
         u.conv, u.bn, u.act, u.x = conv, bn, act, x
         u.desc = conv.desc(N, H, W)
-        u.z = ops.dwconv_fprop(x, conv.w16, u.desc) if kind == 'dw' else ops.conv_fprop(x, conv.w16, u.desc)
-        self._bn_coeffs(u, training)
+        if kind == 'dw':
+            u.w = None
+            u.z = ops.dwconv_fprop(x, conv.w16, u.desc)
+            self._bn_coeffs(u, training)
+        else:
+            u.w = conv.kernel_weights()
+            self._conv_and_coeffs(u, x, u.w, training)
         u.y = ops.bn_apply(u.z, u.scale, u.shift, act, residual=residual)
         return u
 

@@ -316,6 +316,23 @@ def stem_wgrad_from_s2d(dw_s2d, K, C, cpad, dw):
     return dw
 
 
+def group_weight_expand(w32_grouped, K, T, C, groups, out=None):
+    """fp32 [K,T,C/g] -> block-diagonal dense bf16 [K,T,C]."""
+    if out is None:
+        out = torch.empty((K, T, C), device=w32_grouped.device, dtype=bf16)
+    with _T('weight_transpose', 0, 2 * out.numel()):
+        _l.check(_l.load().b200_group_weight_expand(w32_grouped.data_ptr(), K, T, C, groups, out.data_ptr(), _stream()),
+                 "b200_group_weight_expand")
+    return out
+
+
+def group_wgrad_extract(dw_dense, K, T, C, groups, dw_grouped):
+    with _T('weight_transpose', 0, 4 * dw_grouped.numel()):
+        _l.check(_l.load().b200_group_wgrad_extract(dw_dense.data_ptr(), K, T, C, groups, dw_grouped.data_ptr(),
+                                                    _stream()), "b200_group_wgrad_extract")
+    return dw_grouped
+
+
 def cast_bf16(src, dst):
     with _T('cast', 0, 6 * src.numel()):
         _l.check(_l.load().b200_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()),

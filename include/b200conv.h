@@ -145,6 +145,12 @@ int b200_weight_transpose(const void* src, void* dst, int K, int T, int C, b200_
 int b200_stem_weight_to_s2d(const float* w, int K, int C, int Cpad, void* w_s2d, b200_stream_t stream);
 int b200_stem_wgrad_from_s2d(const float* dw_s2d, int K, int C, int Cpad, float* dw, b200_stream_t stream);
 int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, b200_stream_t stream);
+/* grouped convolution (nn.Conv2d(groups=g), models/resnext.py:10-16) through the dense kernels: expand the fp32
+ * master [K][T][C/g] to a block-diagonal dense bf16 [K][T][C]; extract dw_grouped += diagonal blocks of dw_dense */
+int b200_group_weight_expand(const float* w_grouped, int K, int T, int C, int groups, void* w_dense_bf16,
+                             b200_stream_t stream);
+int b200_group_wgrad_extract(const float* dw_dense, int K, int T, int C, int groups, float* dw_grouped,
+                             b200_stream_t stream);
 
 /* ---- loss (csrc/loss.cu) ----------------------------------------------------------------------
  * replaces utils/cross_entropy.py:14-67 (F.cross_entropy / label smoothing) forward+backward.

@@ -59,7 +59,8 @@ def _bn(x, sd, prefix, training, buffers_out, quant):
 
 
 def _conv(x, sd, name, stride, padding, quant):
-    return _q(F.conv2d(x, sd[name + '.weight'], None, stride=stride, padding=padding), quant)
+    w = sd[name + '.weight']
+    return _q(F.conv2d(x, w, None, stride=stride, padding=padding, groups=x.size(1) // w.size(1)), quant)
 
 
 def _block_names(sd, layer):

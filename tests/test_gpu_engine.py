@@ -260,3 +260,18 @@ def test_mobilenet_v2_step():
     with torch.no_grad():
         a, b = mine(x), ref(xq)
     assert _rel(a, b) < 5e-2
+
+
+def test_resnext50_grouped_against_bf16_oracle():
+    """ResNeXt (32 groups, via block-diagonal dense expansion) vs the bf16-emulating oracle."""
+    from convnet.pytorch_b200.models import resnext
+    ref, mine, x, y = _pair(resnext, dict(dataset='imagenet', depth=50), (3, 64, 64), 1000, steps=3, batch=8)
+    _check_against_bf16_oracle(mine, ref, x, y)
+
+
+@pytest.mark.parametrize("size,batch", [(128, 6), (160, 5), (288, 3)])
+def test_resnet50_mixmatch_shapes(size, batch):
+    """Mix&Match input sizes / odd batches (BASELINE config 5): no shape-specialised code path may break."""
+    from convnet.pytorch_b200.models import resnet
+    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=50), (3, size, size), 1000, steps=2, batch=batch)
+    _check_step(ref, mine, x, y, cos_min=0.8, gcos=0.97, grel=0.3)
