@@ -211,6 +211,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_finalize_kernel(
       running_var[c] = (1.f - f) * running_var[c] + f * (float)unbiased;
     }
   }
+  // with a fixed momentum nobody reads the counter, so it can be bumped here; the cumulative mode (momentum < 0)
+  // reads it in every block above and gets a separate, stream-ordered bump kernel instead
+  if (momentum >= 0.f && blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr && running_mean != nullptr)
+    *num_batches_tracked += 1;
 }
 __global__ void bn_bump_kernel(long long* nbt) { *nbt += 1; }
 
@@ -462,7 +466,7 @@ extern "C" int b200_bn_finalize(long long M, int C, const float* gamma, const fl
   bn_finalize_kernel<<<(C + kBnThreads - 1) / kBnThreads, kBnThreads, 0, stream>>>(
       M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd, scale, shift, ws_accum(workspace));
   B200_CHECK_LAUNCH("bn_finalize_kernel");
-  if (nbt != nullptr && running_mean != nullptr) {
+  if (momentum < 0.f && nbt != nullptr && running_mean != nullptr) {
     bn_bump_kernel<<<1, 1, 0, stream>>>(nbt);
     B200_CHECK_LAUNCH("bn_bump_kernel");
   }
