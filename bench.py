@@ -254,17 +254,18 @@ def main():
 
     # ---- per-kernel-class device time of one extra step (CUDA events around every library call) ----
     roof = None
+    ops.start_timing()      # every rank runs the step (it contains the gradient all-reduce); rank 0 reports
+    device_step()
+    torch.cuda.synchronize()
+    classes = ops.stop_timing()
+    sync_all()
     if rank == 0:
-        ops.start_timing()
-        device_step()
-        torch.cuda.synchronize()
-        classes = ops.stop_timing()
         pk = peaks()
         total_ms = sum(c['ms'] for c in classes.values())
         conv_names = [n for n in classes if n.startswith('conv_')]
         conv_ms = sum(classes[n]['ms'] for n in conv_names)
         conv_flops = sum(classes[n]['flops'] for n in conv_names)
-        hbm_names = [n for n in classes if not n.startswith('conv_')]
+        hbm_names = [n for n in classes if not n.startswith('conv_') and n != 'allreduce_nccl']
         hbm_ms = sum(classes[n]['ms'] for n in hbm_names)
         hbm_bytes = sum(classes[n]['bytes'] for n in hbm_names)
         dom = max(classes, key=lambda n: classes[n]['ms'])

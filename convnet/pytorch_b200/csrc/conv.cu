@@ -804,6 +804,12 @@ extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const voi
   if (rc) return rc;
   B200_REQUIRE(x && w && y, B200_ERR_INVALID, "conv_fprop: null pointer");
   B200_REQUIRE(d->C % 8 == 0, B200_ERR_UNSUPPORTED, "conv_fprop: C=%d must be a multiple of 8 (pad the input)", d->C);
+  if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad_h == 1 && d->pad_w == 1 && d->P == d->H && d->Q == d->W &&
+      d->x_pixel_stride == 0 && (!ep || (!ep->bias && !ep->out_fp32)) && halo_eligible(d->H, d->W, d->C, d->K)) {
+    return launch_halo(x, w, y, ep ? ep->residual : nullptr, d->N, d->H, d->W, d->C, d->K, 0, ep ? ep->act : 0,
+                       (ep && ep->bn_stats_workspace) ? reinterpret_cast<double*>(ep->bn_stats_workspace) : nullptr,
+                       (cudaStream_t)stream);
+  }
   IgemmLaunch L;
   memset(&L, 0, sizeof(L));
   L.src = x; L.Nimg = d->N; L.SH = d->H; L.SW = d->W; L.SC = d->C;
@@ -834,6 +840,10 @@ extern "C" int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const vo
   B200_REQUIRE(d->K % 8 == 0, B200_ERR_UNSUPPORTED, "conv_dgrad: K=%d must be a multiple of 8", d->K);
   const int st = d->stride;
   B200_REQUIRE(st == 1 || st == 2, B200_ERR_UNSUPPORTED, "conv_dgrad: stride %d unsupported", st);
+  if (d->R == 3 && d->S == 3 && st == 1 && d->pad_h == 1 && d->pad_w == 1 && d->P == d->H && d->Q == d->W &&
+      halo_eligible(d->H, d->W, d->K, d->C)) {
+    return launch_halo(dy, wt, dx, residual, d->N, d->H, d->W, d->K, d->C, 1, 0, nullptr, stream);
+  }
   // dx[h,w] = sum_{r,s : (h+pad-r) % st == 0} dy[(h+pad-r)/st, (w+pad-s)/st] * w[r,s]
   // one launch per residue class (h % st, w % st); each class is a stride-1 correlation over dy.
   bool any_empty = false;

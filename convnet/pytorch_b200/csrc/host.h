@@ -23,6 +23,11 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn encode_tiled_fn();
 EncodeIm2colFn encode_im2col_fn();
 
+// conv3x3.cu: halo / shift-GEMM path for 3x3 stride-1 pad-1 convolutions
+bool halo_eligible(int H, int W, int Cs, int Nout);
+int launch_halo(const void* src, const void* wmat, void* out, const void* res, int N, int H, int W, int Cs, int Nout,
+                int dir, int act, double* stats, cudaStream_t stream);
+
 inline CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -126,7 +126,10 @@ class Trainer(object):
 
     def _allreduce_gradients(self):
         if self.b200 is not None and self.world_size > 1:
-            dist.all_reduce(self.b200.arena.g32)  # sum; the 1/world factor is folded into the SGD kernel
+            from . import ops
+            g32 = self.b200.arena.g32
+            with ops._T('allreduce_nccl', 0, 4 * g32.numel()):
+                dist.all_reduce(g32)  # sum over ranks; the 1/world factor is folded into the SGD kernel
 
     # ------------------------------------------------------------------ one optimisation step
     def _input_dtype(self):

@@ -35,6 +35,12 @@ CASES = {
     "mb_24_144": (2, 56, 56, 24, 144, 1, 1, 1, 0, {}),
     "mb_144_24": (2, 56, 56, 144, 24, 1, 1, 1, 0, {}),
     "res_relu": (2, 8, 8, 64, 64, 3, 3, 1, 1, {"residual": True, "act": 1}),
+    "halo_28_128": (4, 28, 28, 128, 128, 3, 3, 1, 1, {}),
+    "halo_14_256": (4, 14, 14, 256, 256, 3, 3, 1, 1, {}),
+    "halo_56_res": (2, 56, 56, 64, 64, 3, 3, 1, 1, {"residual": True, "act": 1}),
+    "halo_36_odd": (3, 36, 36, 64, 128, 3, 3, 1, 1, {}),
+    "halo_18_512": (2, 18, 18, 128, 512, 3, 3, 1, 1, {}),
+    "halo_20x12": (3, 20, 12, 64, 64, 3, 3, 1, 1, {}),
 }
 
 
