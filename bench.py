@@ -238,7 +238,14 @@ def main():
         loader = [(x_host, y_host)] * 2
         trainer.forward(loader, training=True)           # warm the path
         sync_all()
-        n_e2e = max(4, args.steps // 2)
+        n_e2e = max(10, args.steps)
+        # raw pinned-host -> device bandwidth of this box (explains e2e when PCIe, not the GPU, is the bound)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        x_host.to(dev, non_blocking=True)
+        h1.record()
+        torch.cuda.synchronize()
+        h2d_ms = h0.elapsed_time(h1)
         loader = [(x_host, y_host)] * n_e2e
         t0 = time.perf_counter()
         trainer.forward(loader, training=True)
@@ -249,6 +256,7 @@ def main():
         e2e = {'value': world * B * n_e2e / float(dt), 'unit': 'images/sec',
                'h2d_bytes_per_step': x_host.numel() * 4 + y_host.numel() * 8,
                'd2h_bytes_per_step': 4 + 2 * 4, 'steps': n_e2e,
+               'h2d_gbs_measured': x_host.numel() * 4 / h2d_ms / 1e6,
                'api': 'Trainer.forward(loader, training=True): H2D of fp32 NCHW batch + loss/prec1/prec5 readback'}
         sync_all()
 
