@@ -19,7 +19,9 @@ constexpr int kBnThreads = 256;
 constexpr int kBnMaxC = 2048;
 constexpr int kBnMaxBlocks = 1184;  // 8 per SM on 148 SMs
 constexpr int kReplicas = 16;         // accumulator copies: spreads same-address fp64 atomics over 16 lines
-constexpr int kWsFloats = kReplicas * 2 * kBnMaxC * 2 + 64;  // replicas x 2*C doubles + ticket counter
+constexpr int kAccumFloats = kReplicas * 2 * kBnMaxC * 2 + 64;  // replicas x 2*C doubles + ticket counter
+constexpr int kMaxPartialBlocks = 6 * 148;                         // backward reduce: per-block partial rows
+constexpr int kWsFloats = kAccumFloats + kMaxPartialBlocks * 2 * kBnMaxC;
 
 struct RowMap {
   int cv, rows_per_iter;
@@ -30,13 +32,25 @@ static inline RowMap make_rowmap(int C) {
   m.rows_per_iter = kBnThreads / m.cv;
   return m;
 }
-static inline int reduce_blocks(long long M, int C, const RowMap& rm) {
+static inline int reduce_blocks(long long M, int C, const RowMap& rm, int resident_per_sm = 6) {
   long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
   long long want = (iters + 7) / 8;          // >= 8 row-iterations per block
   long long cap = 1200000LL / (2 * C);       // bound the number of fp64 atomics (blocks * 2C)
   if (cap < sm_count()) cap = sm_count();
-  static const int per_sm = getenv("B200_BN_REDUCE_BLOCKS_PER_SM") ? atoi(getenv("B200_BN_REDUCE_BLOCKS_PER_SM")) : 6;
-  if (cap > per_sm * sm_count()) cap = per_sm * sm_count();  // few, fat blocks: less same-address atomic traffic at the end
+  static const int env_per_sm = getenv("B200_BN_REDUCE_BLOCKS_PER_SM") ? atoi(getenv("B200_BN_REDUCE_BLOCKS_PER_SM")) : 0;
+  const int per_sm = env_per_sm > 0 ? env_per_sm : resident_per_sm;   // one full wave of fat blocks, no tail wave
+  if (cap > per_sm * sm_count()) cap = per_sm * sm_count();
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+// backward reduce (two-stage, no atomics): one resident wave of fat blocks, each at least 4 row-iterations
+static inline int partial_blocks(long long M, const RowMap& rm, int resident_per_sm) {
+  long long iters = (M + rm.rows_per_iter - 1) / rm.rows_per_iter;
+  long long want = (iters + 3) / 4;
+  static const int env_per_sm = getenv("B200_BN_REDUCE_BLOCKS_PER_SM") ? atoi(getenv("B200_BN_REDUCE_BLOCKS_PER_SM")) : 0;
+  long long cap = (long long)(env_per_sm > 0 ? env_per_sm : resident_per_sm) * sm_count();
+  if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;
@@ -53,6 +67,13 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+// streaming 128-bit load: read-only path, no L1 allocation (every byte is touched once per kernel)
+__device__ __forceinline__ uint4 ld_stream(const __nv_bfloat16* p) {
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  return u;
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -269,99 +290,188 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
   }
 }
 
-// g = dy * act'(.), where the activation argument is y when given, else recomputed as z*scale+shift
-struct MaskSrc {
-  float sc[8], sh[8];
-};
-__device__ __forceinline__ void masked_grad(const float (&dy)[8], const float (&z)[8], const float (&y)[8],
-                                            bool have_y, int act, const MaskSrc& ms, float (&g)[8]) {
+// ---- backward kernels -----------------------------------------------------------------------------
+// Thread mapping: VEC channels per thread (VEC=4: 64-bit accesses, half the per-channel coefficient registers of
+// VEC=8, which is what keeps these 2-read(+1-write) streams at the occupancy of bn_apply; VEC=8 only for C > 1024).
+// g = dy * act'(.), where the activation argument is y when given, else recomputed as z*scale+shift (bit-identical
+// to the forward's fused multiply-add).
+template <int VEC> struct RawVec;
+template <> struct RawVec<4> { uint2 u; };
+template <> struct RawVec<8> { uint4 u; };
+__device__ __forceinline__ RawVec<4> ldv(const __nv_bfloat16* p, RawVec<4>*) {
+  RawVec<4> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.u.x), "=r"(r.u.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ RawVec<8> ldv(const __nv_bfloat16* p, RawVec<8>*) {
+  RawVec<8> r;
+  r.u = ld_stream(p);
+  return r;
+}
+__device__ __forceinline__ void unpackv(const RawVec<4>& r, float (&f)[4]) {
+  const float2 a = unpack_bf16x2(r.u.x), b = unpack_bf16x2(r.u.y);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ void unpackv(const RawVec<8>& r, float (&f)[8]) { unpack8(r.u, f); }
+__device__ __forceinline__ void storev(__nv_bfloat16* p, const float (&f)[4]) {
+  uint2 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void storev(__nv_bfloat16* p, const float (&f)[8]) { store8(p, f); }
+template <int VEC>
+__device__ __forceinline__ void loadfv(const float* p, float (&f)[VEC]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float gi = dy[i];
-    if (act != B200_ACT_NONE) gi *= act_mask(have_y ? y[i] : fmaf(z[i], ms.sc[i], ms.sh[i]), act);
-    g[i] = gi;
+  for (int i = 0; i < VEC; i += 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + i));
+    f[i] = a.x; f[i + 1] = a.y; f[i + 2] = a.z; f[i + 3] = a.w;
   }
 }
 
+// Block partials (VEC channels x 2 statistics per thread) -> fp64 global accumulators; true in the LAST block.
+template <int VEC>
+__device__ __forceinline__ bool accumulate_and_elect_v(float (&acc)[2 * VEC], int cv, int rows_per_iter, int C,
+                                                       double* accum, unsigned* ticket) {
+  __shared__ float red[kBnThreads][2 * VEC + 1];
+  __shared__ bool is_last;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 2 * VEC; ++i) red[t][i] = acc[i];
+  __syncthreads();
+  for (int o = t; o < 2 * C; o += kBnThreads) {
+    const int stat = o / C;
+    const int c = o - stat * C;
+    const int v = c / VEC, e = c - v * VEC;
+    float s = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r) s += red[r * cv + v][stat * VEC + e];
+    atomicAdd(accum + (blockIdx.x % kReplicas) * 2 * C + o, (double)s);
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
 // ---- backward reduce: dbeta = sum g, dgamma = sum g * xhat ------------------------------------------
-__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_reduce_kernel(
+template <int VEC, int ROWS, int MINB, bool NEEDY>
+__global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
     long long M, int C, int cv, int rows_per_iter, int act, const float* __restrict__ mean,
-    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, float* sums,
-    float* dgamma_acc, float* dbeta_acc, double* accum, unsigned* ticket) {
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* __restrict__ partial) {
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
   const int r0 = t / cv, v = t - r0 * cv;
   const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
   const long long row_begin = blockIdx.x * rows_per_block;
   const long long row_end = min(M, row_begin + rows_per_block);
-  const bool have_y = (y != nullptr);
-  float acc[16];
+  float acc[2 * VEC];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 2 * VEC; ++i) acc[i] = 0.f;
   if (active) {
-    float mu[8], is[8];
-    MaskSrc ms;
-    loadf8(mean + v * 8, mu);
-    loadf8(invstd + v * 8, is);
-    if (act != B200_ACT_NONE && !have_y) {
-      float ga[8], be[8];
-      if (gamma) loadf8(gamma + v * 8, ga);
-      if (beta) loadf8(beta + v * 8, be);
+    float mu[VEC], sc[VEC], sh[VEC];
+    loadfv<VEC>(mean + v * VEC, mu);
+    if (!NEEDY && act != B200_ACT_NONE) {
+      float is[VEC];
+      loadfv<VEC>(invstd + v * VEC, is);
+      if (gamma) loadfv<VEC>(gamma + v * VEC, sc);
+      if (beta) loadfv<VEC>(beta + v * VEC, sh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        ms.sc[i] = (gamma ? ga[i] : 1.f) * is[i];
-        ms.sh[i] = (beta ? be[i] : 0.f) - mu[i] * ms.sc[i];
+      for (int i = 0; i < VEC; ++i) {
+        sc[i] = (gamma ? sc[i] : 1.f) * is[i];
+        sh[i] = (beta ? sh[i] : 0.f) - mu[i] * sc[i];
       }
     }
-    const bool need_y = have_y && act != B200_ACT_NONE;
-    for (long long r = row_begin + r0; r < row_end; r += 4LL * rows_per_iter) {
-      uint4 rd[4], rz[4], ry[4];
-      bool ok[4];
+    const long long col = (long long)v * VEC;
+    for (long long r = row_begin + r0; r < row_end; r += (long long)ROWS * rows_per_iter) {
+      RawVec<VEC> rd[ROWS], rz[ROWS], ry[ROWS];
+      bool ok[ROWS];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < ROWS; ++u) {
         const long long rr = r + (long long)u * rows_per_iter;
         ok[u] = rr < row_end;
         if (ok[u]) {
-          rd[u] = *reinterpret_cast<const uint4*>(dy + rr * C + v * 8);
-          rz[u] = *reinterpret_cast<const uint4*>(z + rr * C + v * 8);
-          if (need_y) ry[u] = *reinterpret_cast<const uint4*>(y + rr * C + v * 8);
+          rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
+          rz[u] = ldv(z + rr * C + col, (RawVec<VEC>*)nullptr);
+          if (NEEDY) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < ROWS; ++u) {
         if (!ok[u]) continue;
-        float da[8], za[8], ya[8], ga[8];
-        unpack8(rd[u], da);
-        unpack8(rz[u], za);
-        if (need_y) unpack8(ry[u], ya);
-        masked_grad(da, za, ya, have_y, act, ms, ga);
+        float da[VEC], za[VEC], ya[VEC];
+        unpackv(rd[u], da);
+        unpackv(rz[u], za);
+        if (NEEDY) unpackv(ry[u], ya);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i] += ga[i] * (za[i] - mu[i]) * is[i]; acc[8 + i] += ga[i]; }
+        for (int i = 0; i < VEC; ++i) {
+          float g = da[i];
+          if (act != B200_ACT_NONE) g *= act_mask(NEEDY ? ya[i] : fmaf(za[i], sc[i], sh[i]), act);
+          acc[i] = fmaf(g, za[i] - mu[i], acc[i]);   // the 1/std factor is applied once per channel below
+          acc[VEC + i] += g;
+        }
       }
     }
+    float is[VEC];
+    loadfv<VEC>(invstd + v * VEC, is);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] *= is[i];
   }
-  if (!accumulate_and_elect(acc, cv, rows_per_iter, C, accum, ticket)) return;
-  for (int c = t; c < C; c += kBnThreads) {
-    double d1 = 0.0, d2 = 0.0;
-    for (int rep = 0; rep < kReplicas; ++rep) {
-      d1 += __ldcg(accum + rep * 2 * C + c);
-      d2 += __ldcg(accum + rep * 2 * C + C + c);
-      accum[rep * 2 * C + c] = 0.0;
-      accum[rep * 2 * C + C + c] = 0.0;
-    }
-    const float s1 = (float)d1, s2 = (float)d2;
-    sums[c] = s1;
-    sums[C + c] = s2;
-    if (dgamma_acc) dgamma_acc[c] += s1;
-    if (dbeta_acc) dbeta_acc[c] += s2;
-  }
+  // block partial: fold the rows_per_iter row groups in shared memory, one coalesced row of 2C floats per block
+  __shared__ float red[kBnThreads][2 * VEC + 1];
+#pragma unroll
+  for (int i = 0; i < 2 * VEC; ++i) red[t][i] = acc[i];
   __syncthreads();
-  if (t == 0) *ticket = 0u;
+  float* dst = partial + (size_t)blockIdx.x * 2 * C;
+  for (int o = t; o < 2 * C; o += kBnThreads) {
+    const int stat = o / C;
+    const int c = o - stat * C;
+    const int vv = c / VEC, e = c - vv * VEC;
+    float sacc = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r) sacc += red[r * cv + vv][stat * VEC + e];
+    dst[o] = sacc;
+  }
+}
+
+// second stage: sums[o] = sum over blocks of partial[b][o]  (o in [0, 2C): dgamma then dbeta); a block of 256
+// threads owns 16 outputs x 16 interleaved block groups, fp64 across the groups.
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_final_kernel(const float* __restrict__ partial, int nblocks,
+                                                                          int C, float* __restrict__ sums,
+                                                                          float* dgamma_acc, float* dbeta_acc) {
+  __shared__ double red[16][17];
+  const int lane_o = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const int o = blockIdx.x * 16 + lane_o;
+  double acc = 0.0;
+  if (o < 2 * C) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = grp;
+    for (; b + 48 < nblocks; b += 64) {
+      a0 += __ldcg(partial + (size_t)b * 2 * C + o);
+      a1 += __ldcg(partial + (size_t)(b + 16) * 2 * C + o);
+      a2 += __ldcg(partial + (size_t)(b + 32) * 2 * C + o);
+      a3 += __ldcg(partial + (size_t)(b + 48) * 2 * C + o);
+    }
+    for (; b < nblocks; b += 16) a0 += __ldcg(partial + (size_t)b * 2 * C + o);
+    acc = (double)a0 + (double)a1 + (double)a2 + (double)a3;
+  }
+  red[grp][lane_o] = acc;
+  __syncthreads();
+  if (grp == 0 && o < 2 * C) {
+    double tot = 0.0;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) tot += red[g][lane_o];
+    const float f = (float)tot;
+    sums[o] = f;
+    if (o < C) { if (dgamma_acc) dgamma_acc[o] += f; }
+    else if (dbeta_acc) dbeta_acc[o - C] += f;
+  }
 }
 
 // ---- backward dx --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_dx_kernel(
+template <int VEC, int ROWS, int MINB, bool NEEDY>
+__global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
     long long M, int C, int cv, int rows_per_iter, int act, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -372,60 +482,75 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_dx_kernel(
   const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
   const long long row_begin = blockIdx.x * rows_per_block;
   const long long row_end = min(M, row_begin + rows_per_block);
-  const bool have_y = (y != nullptr);
-  // dz = A*g + B*z + Cc  with A = gamma*istd, B = -gamma*istd^2*dgamma/M, Cc = -A*dbeta/M - B*mean
-  float A[8], B[8], Cc[8];
-  MaskSrc ms;
+  // dz = A*g + B*z + Cc  with A = gamma*istd, B = -gamma*istd^2*dgamma/M, Cc = -A*dbeta/M - B*mean;
+  // the activation argument recomputed from z is z*A + sh
+  float A[VEC], B[VEC], Cc[VEC], sh[VEC];
   {
-    float mu[8], is[8], ga[8], be[8], dg[8], dbt[8];
-    loadf8(mean + v * 8, mu);
-    loadf8(invstd + v * 8, is);
-    if (gamma) loadf8(gamma + v * 8, ga);
-    if (beta) loadf8(beta + v * 8, be);
-    loadf8(sums + v * 8, dg);
-    loadf8(sums + C + v * 8, dbt);
+    float mu[VEC], is[VEC], dg[VEC], dbt[VEC];
+    loadfv<VEC>(mean + v * VEC, mu);
+    loadfv<VEC>(invstd + v * VEC, is);
+    if (gamma) loadfv<VEC>(gamma + v * VEC, A);
+    if (beta) loadfv<VEC>(beta + v * VEC, sh);
+    loadfv<VEC>(sums + v * VEC, dg);
+    loadfv<VEC>(sums + C + v * VEC, dbt);
     const float invM = 1.f / (float)M;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float gm = gamma ? ga[i] : 1.f;
+    for (int i = 0; i < VEC; ++i) {
+      const float gm = gamma ? A[i] : 1.f;
       A[i] = gm * is[i];
       B[i] = -gm * is[i] * is[i] * dg[i] * invM;
       Cc[i] = -A[i] * dbt[i] * invM - B[i] * mu[i];
-      ms.sc[i] = A[i];
-      ms.sh[i] = (beta ? be[i] : 0.f) - mu[i] * A[i];
+      sh[i] = (beta ? sh[i] : 0.f) - mu[i] * A[i];
     }
   }
-  const bool need_y = have_y && act != B200_ACT_NONE;
-  for (long long r = row_begin + r0; r < row_end; r += 4LL * rows_per_iter) {
-    uint4 rd[4], rz[4], ry[4];
-    bool ok[4];
+  const long long col = (long long)v * VEC;
+  for (long long r = row_begin + r0; r < row_end; r += (long long)ROWS * rows_per_iter) {
+    RawVec<VEC> rd[ROWS], rz[ROWS], ry[ROWS];
+    bool ok[ROWS];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < ROWS; ++u) {
       const long long rr = r + (long long)u * rows_per_iter;
       ok[u] = rr < row_end;
       if (ok[u]) {
-        rd[u] = *reinterpret_cast<const uint4*>(dy + rr * C + v * 8);
-        rz[u] = *reinterpret_cast<const uint4*>(z + rr * C + v * 8);
-        if (need_y) ry[u] = *reinterpret_cast<const uint4*>(y + rr * C + v * 8);
+        rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
+        rz[u] = ldv(z + rr * C + col, (RawVec<VEC>*)nullptr);
+        if (NEEDY) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < ROWS; ++u) {
       if (!ok[u]) continue;
       const long long rr = r + (long long)u * rows_per_iter;
-      float da[8], za[8], ya[8], ga[8];
-      unpack8(rd[u], da);
-      unpack8(rz[u], za);
-      if (need_y) unpack8(ry[u], ya);
-      masked_grad(da, za, ya, have_y, act, ms, ga);
+      float da[VEC], za[VEC], ya[VEC];
+      unpackv(rd[u], da);
+      unpackv(rz[u], za);
+      if (NEEDY) unpackv(ry[u], ya);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) za[i] = A[i] * ga[i] + B[i] * za[i] + Cc[i];
-      store8(dz + rr * C + v * 8, za);
-      if (g_out) store8(g_out + rr * C + v * 8, ga);
+      for (int i = 0; i < VEC; ++i) {
+        float g = da[i];
+        if (act != B200_ACT_NONE) g *= act_mask(NEEDY ? ya[i] : fmaf(za[i], A[i], sh[i]), act);
+        da[i] = g;
+        za[i] = A[i] * g + B[i] * za[i] + Cc[i];
+      }
+      storev(dz + rr * C + col, za);
+      if (g_out) storev(g_out + rr * C + col, da);
     }
   }
 }
 
+template <int VEC>
+static inline RowMap make_rowmap_v(int C) {
+  RowMap m;
+  m.cv = C / VEC;
+  m.rows_per_iter = kBnThreads / m.cv;
+  return m;
+}
+
+// tuning knob (measured with tools/bn_bench.py): rows in flight per thread x resident blocks per SM
+static int bwd_variant() {
+  static const int v = getenv("B200_BN_BWD_VARIANT") ? atoi(getenv("B200_BN_BWD_VARIANT")) : 0;
+  return v;
+}
 static int check_c(int C, const char* who) {
   B200_REQUIRE(C > 0 && C % 8 == 0 && C <= kBnMaxC, B200_ERR_UNSUPPORTED,
                "%s: C=%d must be a multiple of 8 and <= %d", who, C, kBnMaxC);
@@ -516,11 +641,38 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const void* z, 
   int rc = check_c(C, "bn_bwd_reduce");
   if (rc) return rc;
   B200_REQUIRE(dy && z && mean && invstd && sums && workspace && M > 0, B200_ERR_INVALID, "bn_bwd_reduce: bad argument");
-  const RowMap rm = make_rowmap(C);
-  bn_bwd_reduce_kernel<<<reduce_blocks(M, C, rm), kBnThreads, 0, (cudaStream_t)stream_>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, act,
-      mean, invstd, gamma, beta, sums, dgamma_acc, dbeta_acc, ws_accum(workspace), ws_ticket(workspace));
+  const bool need_y = (y != nullptr) && act != B200_ACT_NONE;
+#define B200_LAUNCH_RED(VEC, ROWS, MINB)                                                                        \
+  do {                                                                                                          \
+    const RowMap rm = make_rowmap_v<VEC>(C);                                                                    \
+    blocks = partial_blocks(M, rm, MINB);                                                                       \
+    if (need_y)                                                                                                 \
+      bn_bwd_reduce_kernel<VEC, ROWS, MINB, true><<<blocks, kBnThreads, 0, stream>>>(                           \
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv,              \
+          rm.rows_per_iter, act, mean, invstd, gamma, beta, partial);                                           \
+    else                                                                                                        \
+      bn_bwd_reduce_kernel<VEC, ROWS, MINB, false><<<blocks, kBnThreads, 0, stream>>>(                          \
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv,              \
+          rm.rows_per_iter, act, mean, invstd, gamma, beta, partial);                                           \
+  } while (0)
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* partial = workspace + kAccumFloats;
+  int blocks = 0;
+  if (C > 1024) {
+    B200_LAUNCH_RED(8, 2, 3);
+  } else {
+    switch (bwd_variant()) {
+      case 1: B200_LAUNCH_RED(4, 2, 5); break;
+      case 2: B200_LAUNCH_RED(4, 8, 3); break;
+      case 3: B200_LAUNCH_RED(8, 2, 3); break;
+      default: B200_LAUNCH_RED(4, 4, 4); break;
+    }
+  }
+#undef B200_LAUNCH_RED
   B200_CHECK_LAUNCH("bn_bwd_reduce_kernel");
+  bn_bwd_reduce_final_kernel<<<(2 * C + 15) / 16, kBnThreads, 0, stream>>>(partial, blocks, C, sums, dgamma_acc,
+                                                                           dbeta_acc);
+  B200_CHECK_LAUNCH("bn_bwd_reduce_final_kernel");
   return B200_OK;
 }
 
@@ -530,10 +682,31 @@ extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const void* z, long
   int rc = check_c(C, "bn_bwd_dx");
   if (rc) return rc;
   B200_REQUIRE(dy && z && mean && invstd && sums && dz && M > 0, B200_ERR_INVALID, "bn_bwd_dx: bad argument");
-  const RowMap rm = make_rowmap(C);
-  bn_bwd_dx_kernel<<<stream_blocks(M, rm), kBnThreads, 0, (cudaStream_t)stream_>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, act,
-      mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);
+  const bool need_y = (y != nullptr) && act != B200_ACT_NONE;
+#define B200_LAUNCH_DX(VEC, ROWS, MINB)                                                                      \
+  do {                                                                                                       \
+    const RowMap rm = make_rowmap_v<VEC>(C);                                                                 \
+    const int blocks = stream_blocks(M, rm);                                                                 \
+    if (need_y)                                                                                              \
+      bn_bwd_dx_kernel<VEC, ROWS, MINB, true><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(             \
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv,           \
+          rm.rows_per_iter, act, mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);\
+    else                                                                                                     \
+      bn_bwd_dx_kernel<VEC, ROWS, MINB, false><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(            \
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv,           \
+          rm.rows_per_iter, act, mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);\
+  } while (0)
+  if (C > 1024) {
+    B200_LAUNCH_DX(8, 2, 3);
+  } else {
+    switch (bwd_variant()) {
+      case 1: B200_LAUNCH_DX(4, 2, 5); break;
+      case 2: B200_LAUNCH_DX(4, 8, 3); break;
+      case 3: B200_LAUNCH_DX(8, 2, 3); break;
+      default: B200_LAUNCH_DX(4, 4, 4); break;
+    }
+  }
+#undef B200_LAUNCH_DX
   B200_CHECK_LAUNCH("bn_bwd_dx_kernel");
   return B200_OK;
 }
