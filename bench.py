@@ -200,22 +200,26 @@ def main():
         # same sequence as Trainer._step (trainer.py:106-177) with the batch already resident in HBM
         optimizer.zero_grad()
         optimizer.update(0, trainer.training_steps)
-        out = model(x_dev)
-        loss = criterion(out, y_dev)
-        loss.backward()
+        replayed = trainer.graphed_forward_backward(x_dev, y_dev)   # CUDA-graph replay once the shape is warm
+        if replayed is None:
+            out = model(x_dev)
+            loss = criterion(out, y_dev)
+            loss.backward()
+        else:
+            loss = replayed[1]
         trainer._allreduce_gradients()
         optimizer.set_grad_unscale(1.0, world)
         optimizer.step()
         trainer.training_steps += 1
         return loss
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 4)):   # steps 1-2 eager, 3 captures the CUDA graph, 4+ replay it
         device_step()
     sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = lib.launch_count()
+    launches0 = lib.launch_count() + trainer.graph_replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_enq = time.perf_counter()
@@ -225,7 +229,7 @@ def main():
     enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / args.steps     # host time to launch one step (no syncs)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    launches = lib.launch_count() - launches0
+    launches = lib.launch_count() + trainer.graph_replayed_launches - launches0
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -269,6 +273,7 @@ def main():
 
     # ---- per-kernel-class device time of one extra step (CUDA events around every library call) ----
     roof = None
+    trainer.use_graphs = False   # eager launches so that every library call can be bracketed by CUDA events
     ops.start_timing()      # every rank runs the step (it contains the gradient all-reduce); rank 0 reports
     device_step()
     torch.cuda.synchronize()
@@ -316,7 +321,7 @@ def main():
         name = {'resnet': 'ResNet-%d', 'resnext': 'ResNeXt-%d 32x4d', 'mobilenet_v2': 'MobileNet-v2'}[args.model]
         name = name % args.depth if '%d' in name else name
         line = {'metric': '%s images/sec (training step, synthetic %dx%d)' % (name, args.size, args.size), 'value': ips,
-                'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+                'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 4),
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16', 'data': 'synthetic',
                 'config': {'workload': '%s bf16 (fp32 master weights), synthetic ImageNet %dx%d, batch %d/GPU, '

@@ -16,6 +16,7 @@ SURVEY.md section 2.3 C1/C2), and the per-tensor unscale / clip loops of the ref
 (trainer.py:165-172) are folded into the fused optimizer kernel.
 """
 import logging
+import os
 import time
 
 import torch
@@ -23,6 +24,7 @@ import torch.nn as nn
 import torch.distributed as dist
 from torch.nn.utils import clip_grad_norm_
 
+from .utils import regularization
 from .utils.meters import AverageMeter, accuracy
 
 _METERS = ('step', 'data', 'loss', 'prec1', 'prec5')
@@ -98,6 +100,10 @@ class Trainer(object):
         self.loss_scale = loss_scale
         self.adapt_grad_norm = adapt_grad_norm
         self.b200 = getattr(model, '_b200', None)
+        self._graphs, self._graph_pool, self._graph_broken, self._graph_static_ok = {}, None, False, None
+        self.use_graphs = os.environ.get('B200_CUDA_GRAPH', '1') != '0'
+        self.graph_replays = 0                 # bench.py: launches replayed from graphs are not counted by the library
+        self.graph_replayed_launches = 0
         self.world_size = dist.get_world_size() if (distributed and dist.is_initialized()) else 1
 
         if self.b200 is not None:
@@ -131,6 +137,77 @@ class Trainer(object):
             with ops._T('allreduce_nccl', 0, 4 * g32.numel()):
                 dist.all_reduce(g32)  # sum over ranks; the 1/world factor is folded into the SGD kernel
 
+    # ------------------------------------------------------------------ step capture (B200)
+    # The forward + loss + backward of one batch is ~550 kernel launches; issued eagerly from Python they cost
+    # about as much host time as the GPU needs to run them.  After two eager steps per (shape, scale) key the
+    # sequence is captured once into a CUDA graph and replayed.  The optimiser
+    # update and the gradient all-reduce stay outside the graph, so learning-rate schedules keep working.
+    def _graph_eligible(self):
+        if self.b200 is None or not self.use_graphs or self._graph_broken:
+            return False
+        if self._graph_static_ok is None:
+            ok = not any(isinstance(m, nn.Dropout) and m.p > 0 for m in self._model.modules())
+            opt = self.optimizer
+            for o in getattr(opt, 'optim_regime_list', [opt]):
+                reg = getattr(o, 'regularizer', None)
+                for r in getattr(reg, 'regularization_list', []):
+                    # hooks that run between forward and backward cannot be replayed from a graph
+                    if type(r).pre_forward is not regularization.Regularizer.pre_forward or \
+                            type(r).pre_backward is not regularization.Regularizer.pre_backward:
+                        ok = False
+            self._graph_static_ok = ok
+        return self._graph_static_ok
+
+    def graphed_forward_backward(self, inputs, target):
+        """Forward + criterion + backward of one device-resident batch through a captured CUDA graph.
+        Returns (logits, loss) as detached tensors, or None when this call has to run eagerly (warm-up steps of
+        a new shape, unsupported configuration).  Gradients land in the arena exactly as in the eager path."""
+        if not self._graph_eligible() or not inputs.is_cuda:
+            return None
+        key = (tuple(inputs.shape), inputs.dtype, tuple(target.shape), target.dtype, self.loss_scale, self.grad_scale,
+               self._model.training)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = {'seen': 0, 'graph': None}
+        st['seen'] += 1
+        if st['graph'] is None:
+            if st['seen'] <= 2:
+                return None                       # eager warm-up (library handles, allocator, autotuned state)
+            try:
+                self._capture(st, inputs, target)
+            except Exception as e:  # noqa: BLE001  -- keep training eagerly if capture is impossible here
+                logging.warning('B200: CUDA-graph capture failed (%s); continuing with eager launches', e)
+                self._graph_broken = True
+                self._graphs.clear()
+                return None
+        st['x'].copy_(inputs, non_blocking=True)
+        st['y'].copy_(target, non_blocking=True)
+        st['graph'].replay()
+        self.graph_replays += 1
+        self.graph_replayed_launches += st['launches']
+        return st['out'].detach(), st['loss'].detach()
+
+    def _capture(self, st, inputs, target):
+        from . import lib
+        x_s, y_s = torch.empty_like(inputs), torch.empty_like(target)
+        x_s.copy_(inputs)
+        y_s.copy_(target)
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        n0 = lib.launch_count()
+        with torch.cuda.graph(graph, pool=self._graph_pool):
+            out = self.model(x_s)
+            loss = self.criterion(out, y_s)
+            bwd = loss
+            if self.grad_scale is not None:
+                bwd = bwd * self.grad_scale
+            if self.loss_scale is not None:
+                bwd = bwd * self.loss_scale
+            bwd.backward()
+        st.update(graph=graph, x=x_s, y=y_s, out=out, loss=loss, launches=lib.launch_count() - n0)
+
     # ------------------------------------------------------------------ one optimisation step
     def _input_dtype(self):
         return torch.float if self.b200 is not None else self.dtype
@@ -156,6 +233,12 @@ class Trainer(object):
         for i, (inputs, target) in enumerate(chunks):
             target = target.to(self.device, non_blocking=True)
             inputs = inputs.to(self.device, dtype=self._input_dtype(), non_blocking=True)
+            if training and chunk_batch == 1 and not average_output:
+                replayed = self.graphed_forward_backward(inputs, target)
+                if replayed is not None:
+                    outputs.append(replayed[0])
+                    total_loss += float(replayed[1])
+                    continue
             if training:
                 self.optimizer.pre_forward()
             output = self.model(inputs)

@@ -275,3 +275,34 @@ def test_resnet50_mixmatch_shapes(size, batch):
     from convnet.pytorch_b200.models import resnet
     ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=50), (3, size, size), 1000, steps=2, batch=batch)
     _check_step(ref, mine, x, y, cos_min=0.8, gcos=0.97, grel=0.3)
+
+
+def test_trainer_cuda_graph_replay_matches_eager():
+    """Trainer.train on the B200 path replays forward+loss+backward from a CUDA graph after two eager steps;
+    parameters, BN statistics and meters after 6 steps must match a run with graphs disabled."""
+    from convnet.pytorch_b200.models import resnet
+    from convnet.pytorch_b200.engine import convert_b200
+    from convnet.pytorch_b200.trainer import Trainer
+    from convnet.pytorch_b200.utils.optim import OptimRegime
+    from convnet.pytorch_b200.utils.cross_entropy import CrossEntropyLoss
+    _setup()
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(16, 3, 64, 64, generator=g), torch.randint(0, 1000, (16,), generator=g))
+               for _ in range(6)]
+    results = []
+    for use_graphs in (False, True):
+        torch.manual_seed(123)
+        model = resnet(dataset='imagenet', depth=18)
+        convert_b200(model, 'cuda')
+        opt = OptimRegime(model, copy.deepcopy(model.regime))
+        tr = Trainer(model, CrossEntropyLoss().cuda(), opt, device='cuda', print_freq=10 ** 9)
+        tr.use_graphs = use_graphs
+        res = tr.train(batches)
+        assert (tr.graph_replays > 0) == use_graphs, 'graph path %s' % ('not taken' if use_graphs else 'taken')
+        if use_graphs:
+            assert tr.graph_replays == len(batches) - 2 and tr.graph_replayed_launches > 100
+        results.append((res, {k: v.detach().float().clone() for k, v in model.state_dict().items()}))
+    (r0, s0), (r1, s1) = results
+    assert abs(r0['loss'] - r1['loss']) < 2e-3 * max(1.0, abs(r0['loss']))
+    for k in s0:
+        assert _rel(s1[k], s0[k]) < 2e-3, '%s: %.3e' % (k, _rel(s1[k], s0[k]))
