@@ -207,8 +207,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n, 0, 0);
       const uint32_t row_bytes = p.ck * 2;
-      const uint32_t lt = layout_type_for_row_bytes(row_bytes);
-      const uint32_t sbo = 8 * row_bytes;
+      // The issuing thread is latency-bound per instruction: build the descriptor once and advance its address field
+      // (bytes >> 4) instead of re-encoding it for every MMA.
+      const uint64_t proto = make_smem_desc(0, 16, 8 * row_bytes, layout_type_for_row_bytes(row_bytes));
       const int ksteps = p.ck / 16;
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -221,11 +222,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, lt);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, lt);
-            umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          const uint64_t da = proto + (a_addr >> 4);
+          const uint64_t db = proto + ((a_addr + p.a_bytes) >> 4);
+          if (ksteps == 4) {
+            umma_bf16(d_tmem, da, db, idesc, it != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+            umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+            umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+          } else {
+            for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
@@ -501,24 +506,29 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t ltA = layout_type_for_row_bytes(p.ckA * 2);
-        const uint32_t ltB = layout_type_for_row_bytes(p.ckB * 2);
-        const uint32_t sboA = 8 * p.ckA * 2, sboB = 8 * p.ckB * 2;
+        const uint64_t protoA = make_smem_desc(0, p.boxA_bytes, 8 * p.ckA * 2, layout_type_for_row_bytes(p.ckA * 2));
+        const uint64_t protoB = make_smem_desc(0, p.boxB_bytes, 8 * p.ckB * 2, layout_type_for_row_bytes(p.ckB * 2));
+        const uint32_t kincA = (16u * p.ckA * 2) >> 4, kincB = (16u * p.ckB * 2) >> 4;  // 16 pixel rows per K step
         const int boxes_per_mma = min(8, 256 / p.ckB);
         const int ksteps = p.bk / 16;
         for (int b = 0; b < nblk; ++b) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + a_region;
+          const uint64_t da0 = protoA + (a_addr >> 4);
           for (int g0 = 0; g0 < nboxes; g0 += boxes_per_mma) {
             const int nb = min(boxes_per_mma, nboxes - g0);
             const uint32_t idesc = make_idesc_bf16(kTileM, nb * p.ckB, 1, 1);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t da = make_smem_desc(a_addr + k * 16 * p.ckA * 2, p.boxA_bytes, sboA, ltA);
-              const uint64_t db =
-                  make_smem_desc(b_addr + g0 * p.boxB_bytes + k * 16 * p.ckB * 2, p.boxB_bytes, sboB, ltB);
-              umma_bf16(tmem_base + g0 * p.ckB, da, db, idesc, (b | k) != 0 ? 1u : 0u);
+            const uint64_t db0 = protoB + ((a_addr + a_region + g0 * p.boxB_bytes) >> 4);
+            const uint32_t d_tmem = tmem_base + g0 * p.ckB;
+            if (ksteps == 4) {
+              umma_bf16(d_tmem, da0, db0, idesc, b != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, da0 + kincA, db0 + kincB, idesc, 1u);
+              umma_bf16(d_tmem, da0 + 2 * kincA, db0 + 2 * kincB, idesc, 1u);
+              umma_bf16(d_tmem, da0 + 3 * kincA, db0 + 3 * kincB, idesc, 1u);
+            } else {
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, da0 + k * kincA, db0 + k * kincB, idesc, (b | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -804,9 +814,11 @@ extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const voi
   if (rc) return rc;
   B200_REQUIRE(x && w && y, B200_ERR_INVALID, "conv_fprop: null pointer");
   B200_REQUIRE(d->C % 8 == 0, B200_ERR_UNSUPPORTED, "conv_fprop: C=%d must be a multiple of 8 (pad the input)", d->C);
-  if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad_h == 1 && d->pad_w == 1 && d->P == d->H && d->Q == d->W &&
-      d->x_pixel_stride == 0 && (!ep || (!ep->bias && !ep->out_fp32)) && halo_eligible(d->H, d->W, d->C, d->K)) {
-    return launch_halo(x, w, y, ep ? ep->residual : nullptr, d->N, d->H, d->W, d->C, d->K, 0, ep ? ep->act : 0,
+  if (d->stride == 1 && d->pad_h == d->pad_w && d->P == d->H + 2 * d->pad_h - d->R + 1 &&
+      d->Q == d->W + 2 * d->pad_w - d->S + 1 && d->x_pixel_stride == 0 && (!ep || (!ep->bias && !ep->out_fp32)) &&
+      halo_eligible(d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h)) {
+    return launch_halo(x, w, y, ep ? ep->residual : nullptr, d->N, d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h, 0,
+                       ep ? ep->act : 0,
                        (ep && ep->bn_stats_workspace) ? reinterpret_cast<double*>(ep->bn_stats_workspace) : nullptr,
                        (cudaStream_t)stream);
   }
@@ -841,8 +853,8 @@ extern "C" int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const vo
   const int st = d->stride;
   B200_REQUIRE(st == 1 || st == 2, B200_ERR_UNSUPPORTED, "conv_dgrad: stride %d unsupported", st);
   if (d->R == 3 && d->S == 3 && st == 1 && d->pad_h == 1 && d->pad_w == 1 && d->P == d->H && d->Q == d->W &&
-      halo_eligible(d->H, d->W, d->K, d->C)) {
-    return launch_halo(dy, wt, dx, residual, d->N, d->H, d->W, d->K, d->C, 1, 0, nullptr, stream);
+      halo_eligible(d->H, d->W, d->K, d->C, 3, 3, 1)) {
+    return launch_halo(dy, wt, dx, residual, d->N, d->H, d->W, d->K, d->C, 3, 3, 1, 1, 0, nullptr, stream);
   }
   // dx[h,w] = sum_{r,s : (h+pad-r) % st == 0} dy[(h+pad-r)/st, (w+pad-s)/st] * w[r,s]
   // one launch per residue class (h % st, w % st); each class is a stride-1 correlation over dy.
@@ -915,6 +927,15 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   B200_REQUIRE(x && dy && dw, B200_ERR_INVALID, "conv_wgrad: null pointer");
   B200_REQUIRE(d->C % 8 == 0 && d->K % 8 == 0, B200_ERR_UNSUPPORTED,
                "conv_wgrad: C=%d and K=%d must be multiples of 8", d->C, d->K);
+  if (d->stride == 1 && d->pad_h == d->pad_w && d->P == d->H + 2 * d->pad_h - d->R + 1 &&
+      d->Q == d->W + 2 * d->pad_w - d->S + 1 && d->x_pixel_stride == 0 &&
+      halo_wgrad_eligible(d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h)) {
+    // partial tiles of the halo kernel must fit the split-K workspace (units * splits <= SMs, or one split)
+    const int units = (d->C / (d->C == 16 ? 16 : 32)) * ((d->K + kTileM - 1) / kTileM);
+    if (units <= sm_count() + 8)
+      return launch_halo_wgrad(x, dy, dw, workspace, workspace_bytes, d->N, d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h,
+                               stream);
+  }
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.M_total = d->N * d->P * d->Q;

@@ -23,10 +23,16 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn encode_tiled_fn();
 EncodeIm2colFn encode_im2col_fn();
 
-// conv3x3.cu: halo / shift-GEMM path for 3x3 stride-1 pad-1 convolutions
-bool halo_eligible(int H, int W, int Cs, int Nout);
+// conv3x3.cu: halo / shift-GEMM path for stride-1 convolutions (3x3 pad 1; the 4x4 pad 0 space-to-depth stem).
+// H, W are the OUTPUT map dimensions.
+bool halo_geometry_ok(int H, int W, int Cs, int R, int S, int pad);
+bool halo_eligible(int H, int W, int Cs, int Nout, int R, int S, int pad);
 int launch_halo(const void* src, const void* wmat, void* out, const void* res, int N, int H, int W, int Cs, int Nout,
-                int dir, int act, double* stats, cudaStream_t stream);
+                int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream);
+
+bool halo_wgrad_eligible(int H, int W, int C, int K_out, int R, int S, int pad);
+int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t workspace_bytes, int N, int H,
+                      int W, int C, int K_out, int R, int S, int pad, cudaStream_t stream);
 
 inline CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B

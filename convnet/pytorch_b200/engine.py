@@ -24,6 +24,8 @@ from .lib import B200Error, ACT_NONE, ACT_RELU, ACT_RELU6
 
 _ALIGN = 64  # elements; keeps every slot 128B-aligned in the bf16 shadow (TMA needs 16B)
 WIDE_STEM = os.environ.get('B200_WIDE_STEM', '1') != '0'  # overlapping-pixel TMA view for the ImageNet stem
+HALO_STEM = os.environ.get('B200_HALO_STEM', '1') != '0'  # stem fprop on the halo kernel (dense 4x4 description)
+HALO_STEM_WGRAD = os.environ.get('B200_HALO_STEM_WGRAD', '1') != '0'
 FUSE_BN_STATS = os.environ.get('B200_FUSE_BN_STATS', '1') != '0'  # BN statistics in the conv epilogue
 
 
@@ -416,6 +418,13 @@ class ResNetRuntime(Runtime):
                 xs = ops.input_prep(x, 16, s2d=True, border=True)      # [N, Hs+3, Ws+3, 16], data at (+2,+2)
                 desc = ops.make_desc(N, Hs + 3, Ws, 64, K, 4, 1, 1, 0, P=Hs, Q=Ws,
                                      x_strides=(16, (Ws + 3) * 16, (Hs + 3) * (Ws + 3) * 16))
+                st['wgrad_desc'] = desc
+                if HALO_STEM and Ws + 3 <= 128:
+                    # same bordered tensor described as the dense 4x4 / pad-0 convolution it is: the library runs it
+                    # on the halo kernel (one 32-byte-row tile load per output row, weights stationary in smem)
+                    desc = ops.make_desc(N, Hs + 3, Ws + 3, 16, K, 4, 4, 1, 0, P=Hs, Q=Ws)
+                    if HALO_STEM_WGRAD:
+                        st['wgrad_desc'] = desc
             else:
                 xs = ops.input_prep(x, 16, s2d=True)                   # [N, H/2, W/2, 16]
                 desc = ops.make_desc(N, Hs, Ws, 16, K, 4, 4, 1, 2, P=Hs, Q=Ws)
@@ -443,7 +452,7 @@ class ResNetRuntime(Runtime):
         K, Cin = self.stem_conv.out_channels, st['cin']
         if self.imagenet_stem:
             dws = torch.zeros((K, 16, 16), device=self.device, dtype=torch.float32)
-            ops.conv_wgrad(u.x, dz, u.desc, dws)
+            ops.conv_wgrad(u.x, dz, st.get('wgrad_desc', u.desc), dws)
             ops.stem_wgrad_from_s2d(dws, K, Cin, 16, self.stem_g32)
         else:
             dws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.float32)

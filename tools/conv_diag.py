@@ -41,6 +41,10 @@ CASES = {
     "halo_36_odd": (3, 36, 36, 64, 128, 3, 3, 1, 1, {}),
     "halo_18_512": (2, 18, 18, 128, 512, 3, 3, 1, 1, {}),
     "halo_20x12": (3, 20, 12, 64, 64, 3, 3, 1, 1, {}),
+    "halo_stem": (2, 115, 115, 16, 64, 4, 4, 1, 0, {"no_dgrad": True}),
+    "halo_stem_67": (3, 67, 67, 16, 64, 4, 4, 1, 0, {"no_dgrad": True}),
+    "halo_56_128": (2, 56, 56, 128, 64, 3, 3, 1, 1, {}),
+    "halo_8_256": (5, 8, 8, 256, 128, 3, 3, 1, 1, {}),
 }
 
 

@@ -9,6 +9,7 @@ B = 256
 # name: (H, C, K, R, stride, pad)
 LAYERS = {
     'stem_s2d_4x4':     (112, 16, 64, 4, 1, 2),
+    'stem_halo_4x4':    (115, 16, 64, 4, 1, 0),
     'l1_1x1_64_64':     (56, 64, 64, 1, 1, 0),
     'l1_3x3_64_64':     (56, 64, 64, 3, 1, 1),
     'l1_1x1_64_256':    (56, 64, 256, 1, 1, 0),
@@ -31,7 +32,9 @@ LAYERS = {
 def run(name, kinds, once):
     H, C, K, R, stride, pad = LAYERS[name]
     P = None
-    if name.startswith('stem'):
+    if name == 'stem_halo_4x4':
+        desc = ops.make_desc(B, H, H, C, K, R, R, stride, pad)
+    elif name.startswith('stem'):
         desc = ops.make_desc(B, H, H, C, K, R, R, stride, pad, P=H, Q=H)
     else:
         desc = ops.make_desc(B, H, H, C, K, R, R, stride, pad)
