@@ -26,6 +26,7 @@ _ALIGN = 64  # elements; keeps every slot 128B-aligned in the bf16 shadow (TMA n
 WIDE_STEM = os.environ.get('B200_WIDE_STEM', '1') != '0'  # overlapping-pixel TMA view for the ImageNet stem
 HALO_STEM = os.environ.get('B200_HALO_STEM', '1') != '0'  # stem fprop on the halo kernel (dense 4x4 description)
 HALO_STEM_WGRAD = os.environ.get('B200_HALO_STEM_WGRAD', '1') != '0'
+WGRAD_STREAM = os.environ.get('B200_WGRAD_STREAM', '1') != '0'   # weight gradients on a second CUDA stream
 FUSE_BN_STATS = os.environ.get('B200_FUSE_BN_STATS', '1') != '0'  # BN statistics in the conv epilogue
 
 
@@ -191,6 +192,8 @@ class Runtime(object):
         self._anchor = self.arena.slots[0].param
         self._max_c = max([m.num_features for m in model.modules() if isinstance(m, nn.BatchNorm2d)] + [8])
         self._ws = torch.zeros(ops.bn_workspace_floats(self._max_c), device=device, dtype=torch.float32)
+        self._wg_stream = torch.cuda.Stream(device=device) if WGRAD_STREAM else None
+        self._wg_keep = []
         self.loss_scale_inv = 1.0
         self._build()
 
@@ -264,16 +267,38 @@ class Runtime(object):
         dz = ops.bn_bwd_dx(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, g_out=g)
         return dz, g
 
+    # ---- weight gradients on a side stream ----------------------------------------------------------------
+    # wgrad(conv_i) only feeds the optimiser; the critical path of the backward pass is BN-backward -> dgrad of the
+    # units before it.  Launching the wgrads on a second stream lets the tensor/L2-bound wgrad CTAs share the SMs
+    # with the HBM-bound BN kernels of the next unit (inside a captured step the fork/join become graph edges).
+    def _wgrad_async(self, fn, *operands):
+        if self._wg_stream is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self._wg_stream.wait_event(ev)
+        with torch.cuda.stream(self._wg_stream):
+            fn()
+        self._wg_keep.append(operands)   # main-stream allocations: keep them alive (un-reused) until the join
+
+    def _wgrad_join(self):
+        if self._wg_stream is not None and self._wg_keep:
+            torch.cuda.current_stream().wait_stream(self._wg_stream)
+            self._wg_keep = []
+
     def _conv_bwd(self, u, dz, need_dx=True, residual=None):
         """wgrad into the gradient arena and (optionally) dgrad."""
         conv = u.conv
         if conv.groups == 1:
-            ops.conv_wgrad(u.x, dz, u.desc, conv.g32)
+            self._wgrad_async(lambda: ops.conv_wgrad(u.x, dz, u.desc, conv.g32), u.x, dz)
         else:  # dense wgrad into a scratch, then keep the diagonal (group) blocks
-            T = conv.R * conv.S
-            dense = torch.zeros((conv.K, T, conv.C), device=self.device, dtype=torch.float32)
-            ops.conv_wgrad(u.x, dz, u.desc, dense)
-            ops.group_wgrad_extract(dense, conv.K, T, conv.C, conv.groups, conv.g32)
+            def grouped():
+                T = conv.R * conv.S
+                dense = torch.zeros((conv.K, T, conv.C), device=self.device, dtype=torch.float32)
+                ops.conv_wgrad(u.x, dz, u.desc, dense)
+                ops.group_wgrad_extract(dense, conv.K, T, conv.C, conv.groups, conv.g32)
+            self._wgrad_async(grouped, u.x, dz)
         if not need_dx:
             return None
         wt = ops.weight_transpose(u.w)
@@ -318,7 +343,8 @@ class Runtime(object):
         desc = tape['fc_desc']
         dl4 = dl.view(N, 1, 1, self.classes_pad)
         ops.colsum_bf16(dl, self.fc_gb)
-        ops.conv_wgrad(tape['feat'], dl4, desc, self.fc_gw)
+        feat = tape['feat']
+        self._wgrad_async(lambda: ops.conv_wgrad(feat, dl4, desc, self.fc_gw), feat, dl4)
         wt = ops.weight_transpose(self.fc_w16)
         dfeat = ops.conv_dgrad(dl4, wt, desc)
         if tape['mask'] is not None:
@@ -450,14 +476,16 @@ class ResNetRuntime(Runtime):
             dy = ops.maxpool_bwd(dy, st['argmax'], tuple(u.y.shape))
         dz, _ = self._bn_bwd(u, dy, None, ACT_RELU)
         K, Cin = self.stem_conv.out_channels, st['cin']
-        if self.imagenet_stem:
-            dws = torch.zeros((K, 16, 16), device=self.device, dtype=torch.float32)
-            ops.conv_wgrad(u.x, dz, st.get('wgrad_desc', u.desc), dws)
-            ops.stem_wgrad_from_s2d(dws, K, Cin, 16, self.stem_g32)
-        else:
-            dws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.float32)
-            ops.conv_wgrad(u.x, dz, u.desc, dws)
-            self.stem_g32.view(K, 9, Cin).add_(dws[:, :, :Cin])
+        def stem_wgrad():   # every wgrad shares the split-K workspace: all of them go through _wgrad_async
+            if self.imagenet_stem:
+                dws = torch.zeros((K, 16, 16), device=self.device, dtype=torch.float32)
+                ops.conv_wgrad(u.x, dz, st.get('wgrad_desc', u.desc), dws)
+                ops.stem_wgrad_from_s2d(dws, K, Cin, 16, self.stem_g32)
+            else:
+                dws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.float32)
+                ops.conv_wgrad(u.x, dz, u.desc, dws)
+                self.stem_g32.view(K, 9, Cin).add_(dws[:, :, :Cin])
+        self._wgrad_async(stem_wgrad, u.x, dz)
 
     # ---- residual blocks ----------------------------------------------------------------------------
     def _block_fwd(self, spec, x, training):
@@ -511,6 +539,7 @@ class ResNetRuntime(Runtime):
         for spec, saved in zip(reversed(self.blocks), reversed(tape['blocks'])):
             d = self._block_bwd(spec, saved, d)
         self._stem_bwd(tape['stem'], d)
+        self._wgrad_join()
 
 
 class MobileNetRuntime(Runtime):
@@ -594,9 +623,11 @@ class MobileNetRuntime(Runtime):
         u = st['unit']
         dz, _ = self._bn_bwd(u, dy, None, ACT_RELU6)
         K, Cin = self.stem_conv.out_channels, st['cin']
-        dws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.float32)
-        ops.conv_wgrad(u.x, dz, u.desc, dws)
-        self.stem_g32.view(K, 9, Cin).add_(dws[:, :, :Cin])
+        def stem_wgrad():
+            dws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.float32)
+            ops.conv_wgrad(u.x, dz, u.desc, dws)
+            self.stem_g32.view(K, 9, Cin).add_(dws[:, :, :Cin])
+        self._wgrad_async(stem_wgrad, u.x, dz)
 
     def run_forward(self, x, training, want_tape):
         h, stem = self._stem_fwd(x, training)
@@ -624,6 +655,7 @@ class MobileNetRuntime(Runtime):
                 dz, _ = self._bn_bwd(u, d, None, act)
                 d = self._mb_conv_bwd(kind, u, dz, residual=skip if j == 0 else None)
         self._stem_bwd(tape['stem'], d)
+        self._wgrad_join()
 
 
 def convert_b200(model, device=None):

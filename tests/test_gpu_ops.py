@@ -329,3 +329,38 @@ def test_fused_bn_statistics_in_conv_epilogue(N, H, C, K, R):
     for a, b in zip(b0 + [rm0, rv0], b1 + [rm1, rv1]):
         assert rel(b, a) < 1e-5
     assert float(ws.abs().sum()) == 0.0      # the workspace is left zeroed
+
+
+# ---- convolution kernels (im2col igemm, halo shift-GEMM, split-K wgrad) vs fp64 torch on bf16-rounded operands ----
+def _conv_cases():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location(
+        'conv_diag', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'conv_diag.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_CONV_CASE_NAMES = [
+    'c3_64_64_56', 'p1_64_256_56', 'p1_1024_256_14', 'p1s2_256_512', 'c3s2_128_128_56', 'c3_512_512_7',
+    'fc_2048_1000', 'stem_s2d', 'mb_24_144', 'mb_144_24', 'res_relu',
+    # halo (shift-GEMM) path: 3x3 stride 1 at several map sizes / ragged last tile / residual epilogue / stem 4x4
+    'halo_28_128', 'halo_14_256', 'halo_56_res', 'halo_36_odd', 'halo_18_512', 'halo_20x12', 'halo_56_128',
+    'halo_8_256', 'halo_stem', 'halo_stem_67',
+]
+
+
+@pytest.mark.parametrize("case", _CONV_CASE_NAMES)
+def test_conv_fprop_dgrad_wgrad(case):
+    """Tolerances: bf16 outputs (fprop, dgrad) rel-L2 <= 4e-3 (one bf16 rounding of an fp32 accumulator is ~1.7e-3);
+    fp32 weight gradients rel-L2 <= 2e-5, also after a second accumulating call (dw += semantics)."""
+    diag = _conv_cases()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    r = diag.run(case)
+    out_fp32 = diag.CASES[case][9].get('out_fp32', False)
+    assert r['fprop'][0] < (2e-5 if out_fp32 else 4e-3), r
+    if 'dgrad' in r:
+        assert r.get('transpose_ok', True), r
+        assert r['dgrad'][0] < 4e-3, r
+    assert r['wgrad'][0] < 2e-5 and r['wgrad_acc'][0] < 2e-5, r
