@@ -274,6 +274,7 @@ def main():
     # ---- per-kernel-class device time of one extra step (CUDA events around every library call) ----
     roof = None
     trainer.use_graphs = False   # eager launches so that every library call can be bracketed by CUDA events
+    model._b200._wg_stream = None   # ... and on ONE stream (the wgrad side stream would overlap the classes)
     ops.start_timing()      # every rank runs the step (it contains the gradient all-reduce); rank 0 reports
     device_step()
     torch.cuda.synchronize()

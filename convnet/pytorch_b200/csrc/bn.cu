@@ -90,6 +90,12 @@ __device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
+// 1 where the activation passes the gradient, evaluated on the PRE-activation value (same test as act_mask on y)
+__device__ __forceinline__ int act_mask_value(float pre, int act) {
+  if (act == B200_ACT_RELU) return pre > 0.f ? 1 : 0;
+  if (act == B200_ACT_RELU6) return (pre > 0.f && pre < 6.f) ? 1 : 0;
+  return 1;
+}
 __device__ __forceinline__ float act_mask(float v, int act) {
   if (act == B200_ACT_RELU) return v > 0.f ? 1.f : 0.f;
   if (act == B200_ACT_RELU6) return (v > 0.f && v < 6.f) ? 1.f : 0.f;
@@ -254,7 +260,8 @@ template <int MODE>  // 0: none, 1: + residual, 2: + (z2*scale2+shift2)
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
     const __nv_bfloat16* __restrict__ z, long long M, int C, int cv, int rows_per_iter,
     const float* __restrict__ scale, const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
-    const float* __restrict__ scale2, const float* __restrict__ shift2, int act, __nv_bfloat16* __restrict__ y) {
+    const float* __restrict__ scale2, const float* __restrict__ shift2, int act, __nv_bfloat16* __restrict__ y,
+    uint8_t* __restrict__ act_mask) {
   const int t = threadIdx.x;
   if (t >= rows_per_iter * cv) return;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -269,6 +276,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
     const long long ra = r, rb = r + rows_per_iter;
     const bool hb = rb < row_end;
     float fa[8], fb[8], ga[8], gb[8];
+    uint32_t ma = 0, mb = 0;
     load8(z + ra * C + v * 8, fa);
     if (hb) load8(z + rb * C + v * 8, fb);
     if (MODE != 0) {
@@ -281,12 +289,18 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
       float b = hb ? fb[i] * sc[i] + sh[i] : 0.f;
       if (MODE == 1) { a += ga[i]; if (hb) b += gb[i]; }
       if (MODE == 2) { a += ga[i] * sc2[i] + sh2[i]; if (hb) b += gb[i] * sc2[i] + sh2[i]; }
+      ma |= static_cast<uint32_t>(act_mask_value(a, act)) << i;
+      mb |= static_cast<uint32_t>(act_mask_value(b, act)) << i;
       if (act == B200_ACT_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
       if (act == B200_ACT_RELU6) { a = fminf(fmaxf(a, 0.f), 6.f); b = fminf(fmaxf(b, 0.f), 6.f); }
       fa[i] = a; fb[i] = b;
     }
     store8(y + ra * C + v * 8, fa);
     if (hb) store8(y + rb * C + v * 8, fb);
+    if (act_mask != nullptr) {   // one byte per (row, 8-channel vector): bit i = act'(.) of channel v*8+i
+      act_mask[ra * cv + v] = static_cast<uint8_t>(ma);
+      if (hb) act_mask[rb * cv + v] = static_cast<uint8_t>(mb);
+    }
   }
 }
 
@@ -355,12 +369,12 @@ __device__ __forceinline__ bool accumulate_and_elect_v(float (&acc)[2 * VEC], in
 }
 
 // ---- backward reduce: dbeta = sum g, dgamma = sum g * xhat ------------------------------------------
-template <int VEC, int ROWS, int MINB, bool NEEDY>
+template <int VEC, int ROWS, int MINB, int SRC>   // SRC: activation argument 0 recomputed from z, 1 = y, 2 = mask bits
 __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
-    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
-    long long M, int C, int cv, int rows_per_iter, int act, const float* __restrict__ mean,
-    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-    float* __restrict__ partial) {
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const uint8_t* __restrict__ amask,
+    const __nv_bfloat16* __restrict__ z, long long M, int C, int cv, int rows_per_iter, int act,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ partial) {
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -373,7 +387,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
   if (active) {
     float mu[VEC], sc[VEC], sh[VEC];
     loadfv<VEC>(mean + v * VEC, mu);
-    if (!NEEDY && act != B200_ACT_NONE) {
+    if (SRC == 0 && act != B200_ACT_NONE) {
       float is[VEC];
       loadfv<VEC>(invstd + v * VEC, is);
       if (gamma) loadfv<VEC>(gamma + v * VEC, sc);
@@ -387,6 +401,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
     const long long col = (long long)v * VEC;
     for (long long r = row_begin + r0; r < row_end; r += (long long)ROWS * rows_per_iter) {
       RawVec<VEC> rd[ROWS], rz[ROWS], ry[ROWS];
+      uint32_t rm[ROWS];
       bool ok[ROWS];
 #pragma unroll
       for (int u = 0; u < ROWS; ++u) {
@@ -395,7 +410,8 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
         if (ok[u]) {
           rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
           rz[u] = ldv(z + rr * C + col, (RawVec<VEC>*)nullptr);
-          if (NEEDY) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
+          if (SRC == 1) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
+          if (SRC == 2) rm[u] = static_cast<uint32_t>(__ldg(amask + ((rr * C + col) >> 3))) >> (col & 7 & ~(VEC - 1));
         }
       }
 #pragma unroll
@@ -404,11 +420,12 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
         float da[VEC], za[VEC], ya[VEC];
         unpackv(rd[u], da);
         unpackv(rz[u], za);
-        if (NEEDY) unpackv(ry[u], ya);
+        if (SRC == 1) unpackv(ry[u], ya);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           float g = da[i];
-          if (act != B200_ACT_NONE) g *= act_mask(NEEDY ? ya[i] : fmaf(za[i], sc[i], sh[i]), act);
+          if (SRC == 2) g = ((rm[u] >> i) & 1u) ? g : 0.f;
+          else if (act != B200_ACT_NONE) g *= act_mask(SRC == 1 ? ya[i] : fmaf(za[i], sc[i], sh[i]), act);
           acc[i] = fmaf(g, za[i] - mu[i], acc[i]);   // the 1/std factor is applied once per channel below
           acc[VEC + i] += g;
         }
@@ -470,12 +487,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_final_kernel(const f
 }
 
 // ---- backward dx --------------------------------------------------------------------------------
-template <int VEC, int ROWS, int MINB, bool NEEDY>
+template <int VEC, int ROWS, int MINB, int SRC>   // SRC: activation argument 0 recomputed from z, 1 = y, 2 = mask bits
 __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
-    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ z,
-    long long M, int C, int cv, int rows_per_iter, int act, const float* __restrict__ mean,
-    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-    const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out) {
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const uint8_t* __restrict__ amask,
+    const __nv_bfloat16* __restrict__ z, long long M, int C, int cv, int rows_per_iter, int act,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz,
+    __nv_bfloat16* __restrict__ g_out) {
   const int t = threadIdx.x;
   if (t >= rows_per_iter * cv) return;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -506,6 +524,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
   const long long col = (long long)v * VEC;
   for (long long r = row_begin + r0; r < row_end; r += (long long)ROWS * rows_per_iter) {
     RawVec<VEC> rd[ROWS], rz[ROWS], ry[ROWS];
+    uint32_t rm[ROWS];
     bool ok[ROWS];
 #pragma unroll
     for (int u = 0; u < ROWS; ++u) {
@@ -514,7 +533,8 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
       if (ok[u]) {
         rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
         rz[u] = ldv(z + rr * C + col, (RawVec<VEC>*)nullptr);
-        if (NEEDY) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
+        if (SRC == 1) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
+        if (SRC == 2) rm[u] = static_cast<uint32_t>(__ldg(amask + ((rr * C + col) >> 3))) >> (col & 7 & ~(VEC - 1));
       }
     }
 #pragma unroll
@@ -524,11 +544,12 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
       float da[VEC], za[VEC], ya[VEC];
       unpackv(rd[u], da);
       unpackv(rz[u], za);
-      if (NEEDY) unpackv(ry[u], ya);
+      if (SRC == 1) unpackv(ry[u], ya);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         float g = da[i];
-        if (act != B200_ACT_NONE) g *= act_mask(NEEDY ? ya[i] : fmaf(za[i], A[i], sh[i]), act);
+        if (SRC == 2) g = ((rm[u] >> i) & 1u) ? g : 0.f;
+        else if (act != B200_ACT_NONE) g *= act_mask(SRC == 1 ? ya[i] : fmaf(za[i], A[i], sh[i]), act);
         da[i] = g;
         za[i] = A[i] * g + B[i] * za[i] + Cc[i];
       }
@@ -610,7 +631,7 @@ extern "C" int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta,
 
 extern "C" int b200_bn_apply(const void* z, long long M, int C, const float* scale, const float* shift,
                              const void* residual, const void* z2, const float* scale2, const float* shift2, int act,
-                             void* y, b200_stream_t stream_) {
+                             void* y, uint8_t* act_mask, b200_stream_t stream_) {
   int rc = check_c(C, "bn_apply");
   if (rc) return rc;
   B200_REQUIRE(z && scale && shift && y && M > 0, B200_ERR_INVALID, "bn_apply: bad argument");
@@ -623,37 +644,40 @@ extern "C" int b200_bn_apply(const void* z, long long M, int C, const float* sca
   __nv_bfloat16* yy = (__nv_bfloat16*)y;
   if (residual)
     bn_apply_kernel<1><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
-                                                         (const __nv_bfloat16*)residual, nullptr, nullptr, act, yy);
+                                                         (const __nv_bfloat16*)residual, nullptr, nullptr, act, yy, act_mask);
   else if (z2)
     bn_apply_kernel<2><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
-                                                         (const __nv_bfloat16*)z2, scale2, shift2, act, yy);
+                                                         (const __nv_bfloat16*)z2, scale2, shift2, act, yy, act_mask);
   else
     bn_apply_kernel<0><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift, nullptr,
-                                                         nullptr, nullptr, act, yy);
+                                                         nullptr, nullptr, act, yy, act_mask);
   B200_CHECK_LAUNCH("bn_apply_kernel");
   return B200_OK;
 }
 
-extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const void* z, long long M, int C, int act,
+extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M,
+                                  int C, int act,
                                   const float* mean, const float* invstd, const float* gamma, const float* beta,
                                   float* sums, float* dgamma_acc, float* dbeta_acc, float* workspace,
                                   b200_stream_t stream_) {
   int rc = check_c(C, "bn_bwd_reduce");
   if (rc) return rc;
   B200_REQUIRE(dy && z && mean && invstd && sums && workspace && M > 0, B200_ERR_INVALID, "bn_bwd_reduce: bad argument");
-  const bool need_y = (y != nullptr) && act != B200_ACT_NONE;
-#define B200_LAUNCH_RED(VEC, ROWS, MINB)                                                                        \
-  do {                                                                                                          \
-    const RowMap rm = make_rowmap_v<VEC>(C);                                                                    \
-    blocks = partial_blocks(M, rm, MINB);                                                                       \
-    if (need_y)                                                                                                 \
-      bn_bwd_reduce_kernel<VEC, ROWS, MINB, true><<<blocks, kBnThreads, 0, stream>>>(                           \
-          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv,              \
-          rm.rows_per_iter, act, mean, invstd, gamma, beta, partial);                                           \
-    else                                                                                                        \
-      bn_bwd_reduce_kernel<VEC, ROWS, MINB, false><<<blocks, kBnThreads, 0, stream>>>(                          \
-          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv,              \
-          rm.rows_per_iter, act, mean, invstd, gamma, beta, partial);                                           \
+  // activation-argument source: 2 = mask bits, 1 = y, 0 = recomputed from z (or no activation)
+  const int src = (act == B200_ACT_NONE) ? 0 : (act_mask != nullptr ? 2 : (y != nullptr ? 1 : 0));
+#define B200_RED_ARGS(VEC)                                                                                     \
+  (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, act_mask, (const __nv_bfloat16*)z, M, C, rm.cv,           \
+      rm.rows_per_iter, act, mean, invstd, gamma, beta, partial
+#define B200_LAUNCH_RED(VEC, ROWS, MINB)                                                                       \
+  do {                                                                                                         \
+    const RowMap rm = make_rowmap_v<VEC>(C);                                                                   \
+    blocks = partial_blocks(M, rm, MINB);                                                                      \
+    if (src == 2)                                                                                              \
+      bn_bwd_reduce_kernel<VEC, ROWS, MINB, 2><<<blocks, kBnThreads, 0, stream>>>(B200_RED_ARGS(VEC));         \
+    else if (src == 1)                                                                                         \
+      bn_bwd_reduce_kernel<VEC, ROWS, MINB, 1><<<blocks, kBnThreads, 0, stream>>>(B200_RED_ARGS(VEC));         \
+    else                                                                                                       \
+      bn_bwd_reduce_kernel<VEC, ROWS, MINB, 0><<<blocks, kBnThreads, 0, stream>>>(B200_RED_ARGS(VEC));         \
   } while (0)
   cudaStream_t stream = (cudaStream_t)stream_;
   float* partial = workspace + kAccumFloats;
@@ -669,6 +693,7 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const void* z, 
     }
   }
 #undef B200_LAUNCH_RED
+#undef B200_RED_ARGS
   B200_CHECK_LAUNCH("bn_bwd_reduce_kernel");
   bn_bwd_reduce_final_kernel<<<(2 * C + 15) / 16, kBnThreads, 0, stream>>>(partial, blocks, C, sums, dgamma_acc,
                                                                            dbeta_acc);
@@ -676,25 +701,27 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const void* z, 
   return B200_OK;
 }
 
-extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const void* z, long long M, int C, int act,
+extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M, int C,
+                              int act,
                               const float* mean, const float* invstd, const float* gamma, const float* beta,
                               const float* sums, void* dz, void* g_out, b200_stream_t stream_) {
   int rc = check_c(C, "bn_bwd_dx");
   if (rc) return rc;
   B200_REQUIRE(dy && z && mean && invstd && sums && dz && M > 0, B200_ERR_INVALID, "bn_bwd_dx: bad argument");
-  const bool need_y = (y != nullptr) && act != B200_ACT_NONE;
+  const int src = (act == B200_ACT_NONE) ? 0 : (act_mask != nullptr ? 2 : (y != nullptr ? 1 : 0));
+#define B200_DX_ARGS(VEC)                                                                                    \
+  (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, act_mask, (const __nv_bfloat16*)z, M, C, rm.cv,         \
+      rm.rows_per_iter, act, mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out
 #define B200_LAUNCH_DX(VEC, ROWS, MINB)                                                                      \
   do {                                                                                                       \
     const RowMap rm = make_rowmap_v<VEC>(C);                                                                 \
     const int blocks = stream_blocks(M, rm);                                                                 \
-    if (need_y)                                                                                              \
-      bn_bwd_dx_kernel<VEC, ROWS, MINB, true><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(             \
-          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv,           \
-          rm.rows_per_iter, act, mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);\
+    if (src == 2)                                                                                            \
+      bn_bwd_dx_kernel<VEC, ROWS, MINB, 2><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(B200_DX_ARGS(VEC)); \
+    else if (src == 1)                                                                                       \
+      bn_bwd_dx_kernel<VEC, ROWS, MINB, 1><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(B200_DX_ARGS(VEC)); \
     else                                                                                                     \
-      bn_bwd_dx_kernel<VEC, ROWS, MINB, false><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(            \
-          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, M, C, rm.cv,           \
-          rm.rows_per_iter, act, mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);\
+      bn_bwd_dx_kernel<VEC, ROWS, MINB, 0><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(B200_DX_ARGS(VEC)); \
   } while (0)
   if (C > 1024) {
     B200_LAUNCH_DX(8, 2, 3);
@@ -707,6 +734,7 @@ extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const void* z, long
     }
   }
 #undef B200_LAUNCH_DX
+#undef B200_DX_ARGS
   B200_CHECK_LAUNCH("bn_bwd_dx_kernel");
   return B200_OK;
 }

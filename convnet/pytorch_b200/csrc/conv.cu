@@ -597,32 +597,48 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   }
 }
 
-// dw[k][tap][c] += sum over splits of the partial tiles (deterministic order); one thread per 4 channels
+// dw[k][tap][c] += sum over splits of the partial tiles (fixed order => deterministic).  A block owns 32 consecutive
+// float4 outputs; its 8 warps each sum every 8th split (coalesced 512 B reads) and combine through shared memory --
+// with one thread per output the loop over up to 148 splits was a serial chain of L2 round trips.
 __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                                 int K_out, int taps, int C, int ckB, int c_chunks,
                                                                 int boxes_per_cta, int k_tiles, int splits, int pitch) {
+  __shared__ float4 red[8][32];
   const int c4n = C >> 2;
   const long long total = static_cast<long long>(K_out) * taps * c4n;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(idx % c4n) * 4;
-    const int tap = static_cast<int>((idx / c4n) % taps);
-    const int k = static_cast<int>(idx / (static_cast<long long>(c4n) * taps));
-    const int k_tile = k / kTileM, row = k - k_tile * kTileM;
-    const int cc = c / ckB;
-    const int id = tap * c_chunks + cc;
-    const int cgroup = id / boxes_per_cta, x = id - cgroup * boxes_per_cta;
-    const int tile = cgroup * k_tiles + k_tile;
-    const float* src = partial + ((static_cast<long long>(tile) * splits) * kTileM + row) * pitch + x * ckB + (c - cc * ckB);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (long long base = static_cast<long long>(blockIdx.x) * 32; base < total; base += static_cast<long long>(gridDim.x) * 32) {
+    const long long idx = base + lane;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s2 = 0; s2 < splits; ++s2) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(s2) * kTileM * pitch));
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    int c = 0, tap = 0, k = 0;
+    if (idx < total) {
+      c = static_cast<int>(idx % c4n) * 4;
+      tap = static_cast<int>((idx / c4n) % taps);
+      k = static_cast<int>(idx / (static_cast<long long>(c4n) * taps));
+      const int k_tile = k / kTileM, row = k - k_tile * kTileM;
+      const int cc = c / ckB;
+      const int id = tap * c_chunks + cc;
+      const int cgroup = id / boxes_per_cta, x = id - cgroup * boxes_per_cta;
+      const int tile = cgroup * k_tiles + k_tile;
+      const float* src = partial + ((static_cast<long long>(tile) * splits) * kTileM + row) * pitch + x * ckB + (c - cc * ckB);
+      for (int s2 = w; s2 < splits; s2 += nw) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(s2) * kTileM * pitch));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
-    float4* o = reinterpret_cast<float4*>(dw + (static_cast<long long>(k) * taps + tap) * C + c);
-    float4 cur = *o;
-    cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
-    *o = cur;
+    red[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && idx < total) {
+      for (int j = 1; j < nw; ++j) {
+        const float4 v = red[j][lane];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      float4* o = reinterpret_cast<float4*>(dw + (static_cast<long long>(k) * taps + tap) * C + c);
+      float4 cur = *o;
+      cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+      *o = cur;
+    }
+    __syncthreads();
   }
 }
 
@@ -1002,9 +1018,9 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   B200_CHECK_LAUNCH("conv_wgrad_kernel");
   if (p.partial != nullptr) {
     const long long total = static_cast<long long>(d->K) * p.taps_total * (d->C / 4);
-    long long blocks = (total + 255) / 256;
-    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
-    conv_wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p.partial, dw, d->K, p.taps_total, d->C, p.ckB,
+    long long blocks = (total + 31) / 32;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    conv_wgrad_reduce_kernel<<<static_cast<int>(blocks), 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, d->K, p.taps_total, d->C, p.ckB,
                                                                           p.c_chunks, p.boxes_per_cta, p.k_tiles, p.splits,
                                                                           p.pitch);
     B200_CHECK_LAUNCH("conv_wgrad_reduce_kernel");

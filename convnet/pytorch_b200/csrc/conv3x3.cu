@@ -553,29 +553,44 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_co
 }
 
 // dw[k][tap][c] += sum over splits of partial[unit(k_tile, cc)][split][k % 128][tap * cw + c % cw]
+// (same block organisation as conv_wgrad_reduce_kernel: 32 float4 outputs per block, 8 warps over the splits)
 __global__ void __launch_bounds__(256) conv_halo_wgrad_reduce_kernel(const float* __restrict__ partial,
                                                                      float* __restrict__ dw, int K_out, int ntaps, int C,
                                                                      int cw, int k_tiles, int splits, int ncols) {
+  __shared__ float4 red[8][32];
   const int c4n = C >> 2;
   const long long total = static_cast<long long>(K_out) * ntaps * c4n;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(idx % c4n) * 4;
-    const int tap = static_cast<int>((idx / c4n) % ntaps);
-    const int k = static_cast<int>(idx / (static_cast<long long>(c4n) * ntaps));
-    const int k_tile = k >> 7, row = k & 127;
-    const int cc = c / cw;
-    const int unit = cc * k_tiles + k_tile;
-    const float* src = partial + ((static_cast<long long>(unit) * splits) * kHTileM + row) * ncols + tap * cw + (c - cc * cw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (long long base = static_cast<long long>(blockIdx.x) * 32; base < total; base += static_cast<long long>(gridDim.x) * 32) {
+    const long long idx = base + lane;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s2 = 0; s2 < splits; ++s2) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(s2) * kHTileM * ncols));
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    int c = 0, tap = 0, k = 0;
+    if (idx < total) {
+      c = static_cast<int>(idx % c4n) * 4;
+      tap = static_cast<int>((idx / c4n) % ntaps);
+      k = static_cast<int>(idx / (static_cast<long long>(c4n) * ntaps));
+      const int k_tile = k >> 7, row = k & 127;
+      const int cc = c / cw;
+      const int unit = cc * k_tiles + k_tile;
+      const float* src = partial + ((static_cast<long long>(unit) * splits) * kHTileM + row) * ncols + tap * cw + (c - cc * cw);
+      for (int s2 = w; s2 < splits; s2 += nw) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(s2) * kHTileM * ncols));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
-    float4* d = reinterpret_cast<float4*>(dw + (static_cast<long long>(k) * ntaps + tap) * C + c);
-    float4 o = *d;
-    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
-    *d = o;
+    red[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && idx < total) {
+      for (int j = 1; j < nw; ++j) {
+        const float4 v = red[j][lane];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      float4* d = reinterpret_cast<float4*>(dw + (static_cast<long long>(k) * ntaps + tap) * C + c);
+      float4 o = *d;
+      o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+      *d = o;
+    }
+    __syncthreads();
   }
 }
 
@@ -643,9 +658,10 @@ int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace,
     conv_halo_wgrad_kernel<4, 4><<<p.units * p.splits, kWThreads, smem_bytes, stream>>>(tmDy, tmX, p);
   B200_CHECK_LAUNCH("conv_halo_wgrad_kernel");
   const long long total = (long long)K_out * p.ntaps * (C / 4);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  conv_halo_wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, dw, K_out, p.ntaps, C, p.cw, p.k_tiles, p.splits,
+  long long blocks64 = (total + 31) / 32;
+  if (blocks64 > 16LL * sm_count()) blocks64 = 16LL * sm_count();
+  const int blocks = (int)blocks64;
+  conv_halo_wgrad_reduce_kernel<<<blocks, 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, K_out, p.ntaps, C, p.cw, p.k_tiles, p.splits,
                                                             p.ncols);
   B200_CHECK_LAUNCH("conv_halo_wgrad_reduce_kernel");
   return B200_OK;

@@ -1,5 +1,6 @@
 // C-ABI plumbing: error text, launch counter, driver entry points.
 #include "host.h"
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <string.h>
@@ -46,6 +47,14 @@ EncodeTiledFn encode_tiled_fn() {
 EncodeIm2colFn encode_im2col_fn() {
   static EncodeIm2colFn fn = (EncodeIm2colFn)driver_entry("cuTensorMapEncodeIm2col");
   return fn;
+}
+
+int wgrad_reduce_warps(int splits) {
+  static const int env = getenv("B200_WGRAD_REDUCE_WARPS") ? atoi(getenv("B200_WGRAD_REDUCE_WARPS")) : 0;
+  int w = env > 0 ? env : 8;
+  if (w > 8) w = 8;
+  while (w > 1 && w > splits) w >>= 1;   // no idle warps when there are only a few splits
+  return w;
 }
 
 }  // namespace b200

@@ -34,6 +34,9 @@ bool halo_wgrad_eligible(int H, int W, int C, int K_out, int R, int S, int pad);
 int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t workspace_bytes, int N, int H,
                       int W, int C, int K_out, int R, int S, int pad, cudaStream_t stream);
 
+// warps of a split-K reduce block that share the loop over the splits (1..8)
+int wgrad_reduce_warps(int splits);
+
 inline CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -27,6 +27,7 @@ WIDE_STEM = os.environ.get('B200_WIDE_STEM', '1') != '0'  # overlapping-pixel TM
 HALO_STEM = os.environ.get('B200_HALO_STEM', '1') != '0'  # stem fprop on the halo kernel (dense 4x4 description)
 HALO_STEM_WGRAD = os.environ.get('B200_HALO_STEM_WGRAD', '1') != '0'
 WGRAD_STREAM = os.environ.get('B200_WGRAD_STREAM', '1') != '0'   # weight gradients on a second CUDA stream
+BN_ACT_MASK = os.environ.get('B200_BN_ACT_MASK', '0') != '0'    # 1-bit activation masks for residual joins (measured: not a win)
 FUSE_BN_STATS = os.environ.get('B200_FUSE_BN_STATS', '1') != '0'  # BN statistics in the conv epilogue
 
 
@@ -177,7 +178,7 @@ class _BN(object):
 
 class _Unit(object):
     """saved state of one conv+BN unit for backward."""
-    __slots__ = ('x', 'z', 'y', 'w', 'desc', 'mean', 'invstd', 'scale', 'shift', 'sums', 'conv', 'bn', 'act')
+    __slots__ = ('x', 'z', 'y', 'w', 'desc', 'mean', 'invstd', 'scale', 'shift', 'sums', 'conv', 'bn', 'act', 'mask')
 
 
 class Runtime(object):
@@ -214,10 +215,16 @@ class Runtime(object):
         u.desc = conv.desc(N, H, W)
         u.w = conv.kernel_weights()
         self._conv_and_coeffs(u, x, u.w, training)
+        # a join (something is added before the activation) cannot recompute act'(.) from z alone: keep one bit per
+        # element instead of re-reading the bf16 output in both backward kernels
+        u.mask = None
+        if BN_ACT_MASK and tape and training and act != ACT_NONE and (other is not None or residual is not None):
+            u.mask = torch.empty(u.z.numel() // 8, device=self.device, dtype=torch.uint8)
         if other is not None:
-            u.y = ops.bn_apply(u.z, u.scale, u.shift, act, z2=other.z, scale2=other.scale, shift2=other.shift)
+            u.y = ops.bn_apply(u.z, u.scale, u.shift, act, z2=other.z, scale2=other.scale, shift2=other.shift,
+                               act_mask=u.mask)
         else:
-            u.y = ops.bn_apply(u.z, u.scale, u.shift, act, residual=residual)
+            u.y = ops.bn_apply(u.z, u.scale, u.shift, act, residual=residual, act_mask=u.mask)
         return u
 
     def _conv_and_coeffs(self, u, x, w16, training):
@@ -261,10 +268,11 @@ class Runtime(object):
         """BN (+activation) backward of unit u: returns dz (and g = dy*act'(.) when want_g).
         y_mask=None with an activation: the mask is recomputed from z inside the kernels (no read of y)."""
         bn = u.bn
+        mask = getattr(u, 'mask', None) if y_mask is not None else None
         ops.bn_bwd_reduce(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, bn.dgamma, bn.dbeta,
-                          self._ws)
+                          self._ws, act_mask=mask)
         g = torch.empty_like(dy) if want_g else None
-        dz = ops.bn_bwd_dx(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, g_out=g)
+        dz = ops.bn_bwd_dx(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, g_out=g, act_mask=mask)
         return dz, g
 
     # ---- weight gradients on a side stream ----------------------------------------------------------------

@@ -46,9 +46,9 @@ SIGNATURES = {
     "b200_bn_stats": [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_bn_finalize": [_ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_bn_eval_coeffs": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp],
-    "b200_bn_apply": [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
-    "b200_bn_bwd_reduce": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "b200_bn_bwd_dx": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200_bn_apply": [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "b200_bn_bwd_reduce": [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200_bn_bwd_dx": [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_maxpool3x3s2_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "b200_maxpool3x3s2_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b200_avgpool_fwd": [_vp, _i, _i, _i, _vp, _vp],

@@ -202,38 +202,46 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, scale, shift):
                                            _stream()), "b200_bn_eval_coeffs")
 
 
-def bn_apply(z, scale, shift, act=ACT_NONE, residual=None, z2=None, scale2=None, shift2=None, out=None):
+def bn_apply(z, scale, shift, act=ACT_NONE, residual=None, z2=None, scale2=None, shift2=None, out=None, act_mask=None):
+    """act_mask: optional uint8 tensor of z.numel()/8 bytes receiving one act'(.) bit per element (bn_bwd_* read it
+    instead of y)."""
     C = z.shape[-1]
     M = z.numel() // C
-    _chk(z, bf16, "z"); _chk(residual, bf16, "residual"); _chk(z2, bf16, "z2")
+    _chk(z, bf16, "z"); _chk(residual, bf16, "residual"); _chk(z2, bf16, "z2"); _chk(act_mask, torch.uint8, "act_mask")
+    if act_mask is not None and act_mask.numel() * 8 != z.numel():
+        raise _l.B200Error("act_mask must hold z.numel()/8 bytes")
     if out is None:
         out = torch.empty_like(z)
     with _T('bn_apply', 0, 2 * z.numel() * (2 + (residual is not None) + (z2 is not None))):
         _l.check(_l.load().b200_bn_apply(z.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), _l.ptr(residual),
-                                         _l.ptr(z2), _l.ptr(scale2), _l.ptr(shift2), int(act), out.data_ptr(), _stream()),
+                                         _l.ptr(z2), _l.ptr(scale2), _l.ptr(shift2), int(act), out.data_ptr(),
+                                         _l.ptr(act_mask), _stream()),
                  "b200_bn_apply")
     return out
 
 
-def bn_bwd_reduce(dy, y, z, act, mean, invstd, gamma, beta, sums, dgamma_acc, dbeta_acc, workspace):
-    """y=None: the activation mask is recomputed from z (valid when nothing was added before the activation)."""
+def bn_bwd_reduce(dy, y, z, act, mean, invstd, gamma, beta, sums, dgamma_acc, dbeta_acc, workspace, act_mask=None):
+    """y=None and act_mask=None: the activation mask is recomputed from z (valid when nothing was added before the
+    activation); act_mask (bits written by bn_apply) takes precedence over y."""
     C = z.shape[-1]
     M = z.numel() // C
-    _chk(dy, bf16, "dy"); _chk(y, bf16, "y"); _chk(z, bf16, "z")
-    with _T('bn_bwd_reduce', 0, 2 * z.numel() * (2 + (y is not None))):
-        _l.check(_l.load().b200_bn_bwd_reduce(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
+    _chk(dy, bf16, "dy"); _chk(y, bf16, "y"); _chk(z, bf16, "z"); _chk(act_mask, torch.uint8, "act_mask")
+    with _T('bn_bwd_reduce', 0, 2 * z.numel() * (2 + (y is not None and act_mask is None))):
+        _l.check(_l.load().b200_bn_bwd_reduce(dy.data_ptr(), _l.ptr(y), _l.ptr(act_mask), z.data_ptr(), M, C, int(act),
+                                              mean.data_ptr(),
                                               invstd.data_ptr(), _l.ptr(gamma), _l.ptr(beta), sums.data_ptr(),
                                               _l.ptr(dgamma_acc), _l.ptr(dbeta_acc), workspace.data_ptr(), _stream()),
                  "b200_bn_bwd_reduce")
 
 
-def bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, beta, sums, dz=None, g_out=None):
+def bn_bwd_dx(dy, y, z, act, mean, invstd, gamma, beta, sums, dz=None, g_out=None, act_mask=None):
     C = z.shape[-1]
     M = z.numel() // C
     if dz is None:
         dz = torch.empty_like(z)
-    with _T('bn_bwd_dx', 0, 2 * z.numel() * (3 + (y is not None) + (g_out is not None))):
-        _l.check(_l.load().b200_bn_bwd_dx(dy.data_ptr(), _l.ptr(y), z.data_ptr(), M, C, int(act), mean.data_ptr(),
+    with _T('bn_bwd_dx', 0, 2 * z.numel() * (3 + (y is not None and act_mask is None) + (g_out is not None))):
+        _l.check(_l.load().b200_bn_bwd_dx(dy.data_ptr(), _l.ptr(y), _l.ptr(act_mask), z.data_ptr(), M, C, int(act),
+                                          mean.data_ptr(),
                                           invstd.data_ptr(), _l.ptr(gamma), _l.ptr(beta), sums.data_ptr(),
                                           dz.data_ptr(), _l.ptr(g_out), _stream()), "b200_bn_bwd_dx")
     return dz

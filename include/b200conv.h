@@ -107,19 +107,21 @@ int b200_bn_finalize(long long M, int C, const float* gamma, const float* beta, 
 int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float* scale, float* shift, b200_stream_t stream);
 /* y = act(z*scale+shift + [residual | z2*scale2+shift2]) */
+/* act_mask (nullable, M*C/8 bytes): bit c%8 of byte (row*C + c)/8 = act'(.) of that element (1 where the
+ * activation passes the gradient).  The backward kernels accept it instead of y: 1 bit instead of 16 per element. */
 int b200_bn_apply(const void* z, long long M, int C, const float* scale, const float* shift,
                   const void* residual, const void* z2, const float* scale2, const float* shift2,
-                  int act, void* y, b200_stream_t stream);
-/* g = dy * act'(a) where a = y when y != NULL (needed when a residual was added before the activation),
- * else a is recomputed as z*gamma*invstd + (beta - mean*gamma*invstd), which saves reading y.
+                  int act, void* y, uint8_t* act_mask, b200_stream_t stream);
+/* g = dy * act'(a): from act_mask bits when act_mask != NULL, else a = y when y != NULL (a residual was added
+ * before the activation), else a is recomputed as z*gamma*invstd + (beta - mean*gamma*invstd) (no read of y).
  * dgamma/dbeta: per-layer sums written to sums[0..C) (dgamma) sums[C..2C) (dbeta) and ACCUMULATED into
  * dgamma_acc/dbeta_acc (gradient arena).  The workspace must be zero before its first use (the kernels
  * leave it zeroed) and must not be shared between concurrently running streams. */
-int b200_bn_bwd_reduce(const void* dy, const void* y, const void* z, long long M, int C, int act,
+int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M, int C, int act,
                        const float* mean, const float* invstd, const float* gamma, const float* beta,
                        float* sums, float* dgamma_acc, float* dbeta_acc, float* workspace, b200_stream_t stream);
 /* dz = gamma*invstd*(g - dbeta/M - xhat*dgamma/M); optionally also writes g (bf16) for the skip path */
-int b200_bn_bwd_dx(const void* dy, const void* y, const void* z, long long M, int C, int act,
+int b200_bn_bwd_dx(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M, int C, int act,
                    const float* mean, const float* invstd, const float* gamma, const float* beta,
                    const float* sums, void* dz, void* g_out, b200_stream_t stream);
 

@@ -77,6 +77,26 @@ def test_bn_forward_backward(M, C, act):
     ops.bn_bwd_reduce(dy, y, z, act, mean, invstd, gamma, beta, sums, dgam, dbet, ws)
     torch.cuda.synchronize()
     assert rel(dgam, 2 * dgam_ref) < tol
+    # 1-bit activation masks written by bn_apply replace y in both backward kernels.  The bits test the fp32
+    # PRE-activation value (like torch's relu/hardtanh backward); they may differ from the mask derived from the
+    # bf16-rounded output only where the output rounds onto a clamp boundary.
+    bits = torch.zeros(M * C // 8, dtype=torch.uint8).cuda()
+    y2 = ops.bn_apply(z, scale, shift, act, residual=res, act_mask=bits)
+    assert torch.equal(y2, y)
+    shifts = torch.arange(8, device='cuda', dtype=torch.int32)
+    mask2 = ((bits.view(M, C // 8, 1).to(torch.int32) >> shifts) & 1).view(M, C).double()
+    assert float((mask2 != mask).double().mean()) < 2e-3
+    if act != 2:
+        assert torch.equal(mask2, mask)
+    gd2 = dy.double() * mask2
+    sums2, dg2, db2 = torch.empty(2 * C).cuda(), torch.zeros(C).cuda(), torch.zeros(C).cuda()
+    ops.bn_bwd_reduce(dy, None, z, act, mean, invstd, gamma, beta, sums2, dg2, db2, ws, act_mask=bits)
+    gout2 = torch.empty_like(dy)
+    dz2 = ops.bn_bwd_dx(dy, None, z, act, mean, invstd, gamma, beta, sums2, g_out=gout2, act_mask=bits)
+    torch.cuda.synchronize()
+    dzd2 = torch.autograd.grad(pre_lin, [zd], gd2)[0]
+    assert rel(dg2, (gd2 * xhat.detach()).sum(0)) < tol and rel(db2, gd2.sum(0)) < tol
+    assert close_bf16(dz2, dzd2) and close_bf16(gout2, gd2)
 
 
 def test_bn_dual_apply_and_eval():
