@@ -208,20 +208,29 @@ __global__ void __launch_bounds__(kBnThreads) bn_finalize_kernel(
     long long M, int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
     float* running_mean, float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale,
     float* shift, double* accum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // 16 lanes per channel, one per accumulator replica (a serial loop over the replicas was a chain of L2 round
+  // trips in a kernel that sits on the critical path between the convolution and the BN apply)
+  static_assert(kReplicas == 16, "lane mapping below assumes 16 replicas");
+  const int rep = threadIdx.x & 15;
+  const int c = blockIdx.x * (kBnThreads / 16) + (threadIdx.x >> 4);
   float f = momentum;
   if (momentum < 0.f) {
     const long long nbt = num_batches_tracked ? *num_batches_tracked : 0;
     f = 1.f / (float)(nbt + 1);
   }
+  double s1 = 0.0, s2 = 0.0;
   if (c < C) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int rep = 0; rep < kReplicas; ++rep) {
-      s1 += accum[rep * 2 * C + c];
-      s2 += accum[rep * 2 * C + C + c];
-      accum[rep * 2 * C + c] = 0.0;
-      accum[rep * 2 * C + C + c] = 0.0;
-    }
+    s1 = accum[rep * 2 * C + c];
+    s2 = accum[rep * 2 * C + C + c];
+    accum[rep * 2 * C + c] = 0.0;
+    accum[rep * 2 * C + C + c] = 0.0;
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (c < C && rep == 0) {
     const double mu = s1 / (double)M;
     double var = s2 / (double)M - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -453,32 +462,33 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
 }
 
 // second stage: sums[o] = sum over blocks of partial[b][o]  (o in [0, 2C): dgamma then dbeta); a block of 256
-// threads owns 16 outputs x 16 interleaved block groups, fp64 across the groups.
+// threads owns 4 outputs x 64 interleaved block groups (every load independent: the kernel is pure latency),
+// fp64 across the groups.
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_final_kernel(const float* __restrict__ partial, int nblocks,
                                                                           int C, float* __restrict__ sums,
                                                                           float* dgamma_acc, float* dbeta_acc) {
-  __shared__ double red[16][17];
-  const int lane_o = threadIdx.x & 15, grp = threadIdx.x >> 4;
-  const int o = blockIdx.x * 16 + lane_o;
+  __shared__ double red[64][5];
+  const int lane_o = threadIdx.x & 3, grp = threadIdx.x >> 2;
+  const int o = blockIdx.x * 4 + lane_o;
   double acc = 0.0;
   if (o < 2 * C) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int b = grp;
-    for (; b + 48 < nblocks; b += 64) {
+    for (; b + 192 < nblocks; b += 256) {
       a0 += __ldcg(partial + (size_t)b * 2 * C + o);
-      a1 += __ldcg(partial + (size_t)(b + 16) * 2 * C + o);
-      a2 += __ldcg(partial + (size_t)(b + 32) * 2 * C + o);
-      a3 += __ldcg(partial + (size_t)(b + 48) * 2 * C + o);
+      a1 += __ldcg(partial + (size_t)(b + 64) * 2 * C + o);
+      a2 += __ldcg(partial + (size_t)(b + 128) * 2 * C + o);
+      a3 += __ldcg(partial + (size_t)(b + 192) * 2 * C + o);
     }
-    for (; b < nblocks; b += 16) a0 += __ldcg(partial + (size_t)b * 2 * C + o);
+    for (; b < nblocks; b += 64) a0 += __ldcg(partial + (size_t)b * 2 * C + o);
     acc = (double)a0 + (double)a1 + (double)a2 + (double)a3;
   }
   red[grp][lane_o] = acc;
   __syncthreads();
   if (grp == 0 && o < 2 * C) {
     double tot = 0.0;
-#pragma unroll
-    for (int g = 0; g < 16; ++g) tot += red[g][lane_o];
+#pragma unroll 8
+    for (int g = 0; g < 64; ++g) tot += red[g][lane_o];
     const float f = (float)tot;
     sums[o] = f;
     if (o < C) { if (dgamma_acc) dgamma_acc[o] += f; }
@@ -609,7 +619,7 @@ extern "C" int b200_bn_finalize(long long M, int C, const float* gamma, const fl
   B200_REQUIRE(mean && invstd && scale && shift && workspace && M > 0, B200_ERR_INVALID, "bn_finalize: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   // NOTE: momentum < 0 reads *nbt before the bump below (same stream => ordered)
-  bn_finalize_kernel<<<(C + kBnThreads - 1) / kBnThreads, kBnThreads, 0, stream>>>(
+  bn_finalize_kernel<<<(C + 15) / 16, kBnThreads, 0, stream>>>(
       M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd, scale, shift, ws_accum(workspace));
   B200_CHECK_LAUNCH("bn_finalize_kernel");
   if (momentum < 0.f && nbt != nullptr && running_mean != nullptr) {
@@ -695,7 +705,7 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* 
 #undef B200_LAUNCH_RED
 #undef B200_RED_ARGS
   B200_CHECK_LAUNCH("bn_bwd_reduce_kernel");
-  bn_bwd_reduce_final_kernel<<<(2 * C + 15) / 16, kBnThreads, 0, stream>>>(partial, blocks, C, sums, dgamma_acc,
+  bn_bwd_reduce_final_kernel<<<(2 * C + 3) / 4, kBnThreads, 0, stream>>>(partial, blocks, C, sums, dgamma_acc,
                                                                            dbeta_acc);
   B200_CHECK_LAUNCH("bn_bwd_reduce_final_kernel");
   return B200_OK;

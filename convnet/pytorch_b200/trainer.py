@@ -146,7 +146,7 @@ class Trainer(object):
         if self.b200 is None or not self.use_graphs or self._graph_broken:
             return False
         if self._graph_static_ok is None:
-            ok = not any(isinstance(m, nn.Dropout) and m.p > 0 for m in self._model.modules())
+            ok = True    # dropout is fine: the mask comes from torch's graph-safe CUDA generator (philox offsets advance per replay)
             opt = self.optimizer
             for o in getattr(opt, 'optim_regime_list', [opt]):
                 reg = getattr(o, 'regularizer', None)
