@@ -13,6 +13,7 @@
 // 226-227) and its autograd backward (trainer.py:162).
 #include "common.cuh"
 #include "host.h"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -47,6 +48,7 @@ struct IgemmParams {
   int act, out_fp32;
   int tma_store;         // 1: dense bf16 output staged in smem and written by TMA (tmC), residual via tmR
   int plain_a;           // 1: A is a dense [M_total, SC] matrix (1x1, stride 1, no padding): tiled TMA
+  int b_stationary;      // 1: every (tap, k-block) weight slice stays in shared memory (small 1x1 layers): only A streams
   double* stats;         // fused BN statistics accumulators [kStatReplicas][2][N_total] (BN workspace) or nullptr
   void* out;
   const void* res;
@@ -130,20 +132,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
-  __shared__ __align__(8) uint64_t res_bar;
+  __shared__ __align__(8) uint64_t res_bar, bstat_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  const uint32_t stage_bytes = p.b_stationary ? p.a_bytes : p.a_bytes + p.b_bytes;
+  uint8_t* sBstat = smem + p.num_stages * stage_bytes;   // stationary weight slices [tap * c_chunks + k-block]
+  uint8_t* epi_base = sBstat + (p.b_stationary ? static_cast<uint32_t>(p.ntaps * p.c_chunks) * p.b_bytes : 0u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(&bstat_bar, 1);
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 8);
@@ -174,6 +179,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const int IJ = p.I * p.J;
+      if (p.b_stationary && blockIdx.x < total_tiles) {   // n_tiles == 1: the same slices serve every tile of the CTA
+        mbar_arrive_expect_tx(&bstat_bar, static_cast<uint32_t>(k_iters) * (p.tx_bytes - p.a_bytes));
+        for (int t = 0; t < p.ntaps; ++t)
+          for (int cc = 0; cc < p.c_chunks; ++cc)
+            tma_load_3d(&tmB, &bstat_bar, sBstat + (t * p.c_chunks + cc) * p.b_bytes, cc * p.ck, p.taps[t].b_tap, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
@@ -190,12 +201,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + p.a_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
+            mbar_arrive_expect_tx(&full_bar[stage], p.b_stationary ? p.a_bytes : p.tx_bytes);
             if (p.plain_a)  // 1x1 / stride 1: the A operand is a dense [M, C] matrix -> tiled TMA (faster than im2col)
               tma_load_2d(&tmA, &full_bar[stage], sa, cc * p.ck, m0);
             else
               tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cc * p.ck, base_w, base_h, img, te.off_w, te.off_h);
-            tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.ck, te.b_tap, n_tile * p.block_n);
+            if (!p.b_stationary) tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.ck, te.b_tap, n_tile * p.block_n);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -211,6 +222,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // (bytes >> 4) instead of re-encoding it for every MMA.
       const uint64_t proto = make_smem_desc(0, 16, 8 * row_bytes, layout_type_for_row_bytes(row_bytes));
       const int ksteps = p.ck / 16;
+      if (p.b_stationary && blockIdx.x < total_tiles) {
+        mbar_wait(&bstat_bar, 0);
+        tc_fence_after();
+      }
+      const uint32_t bstat_addr = smem_u32(sBstat);
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const int acc = local & 1;
@@ -223,7 +239,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint64_t da = proto + (a_addr >> 4);
-          const uint64_t db = proto + ((a_addr + p.a_bytes) >> 4);
+          const uint64_t db = proto + ((p.b_stationary ? bstat_addr + it * p.b_bytes : a_addr + p.a_bytes) >> 4);
           if (ksteps == 4) {
             umma_bf16(d_tmem, da, db, idesc, it != 0 ? 1u : 0u);
             umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
@@ -273,7 +289,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // clipped at the M tail); the residual tile is fetched by TMA into the same buffer and updated in place.
         const bool leader = (warp == 2 && lane == 0);
         const int row = q * 32 + lane;
-        uint8_t* epi = smem + p.num_stages * stage_bytes;
+        uint8_t* epi = epi_base;
         const int nbox = p.block_n >> 6;
         if (leader && local > 0) bulk_wait_group_read0();  // previous tile's store has finished reading smem
         named_bar_sync(1, 256);
@@ -756,7 +772,16 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.tma_store = (L.os == 1 && !L.out_fp32 && (p.block_n % 64) == 0 && (L.Nout % p.block_n) == 0 && L.ldo == L.Nout &&
                  L.OH == L.I && L.OW == L.J && L.oh0 == 0 && L.ow0 == 0) ? 1 : 0;
   const int epi_bytes = p.tma_store ? kTileM * p.block_n * 2 : 0;
-  p.num_stages = (kSmemBudget - epi_bytes) / (int)stage;
+  // small 1x1 layers (all weight slices <= 64 KB): keep the weights resident, stream only the activations
+  static const bool bstat_enabled = !(getenv("B200_IGEMM_BSTAT") && atoi(getenv("B200_IGEMM_BSTAT")) == 0);
+  const int b_all = L.ntaps * p.c_chunks * (int)p.b_bytes;
+  int bstat_bytes = 0;
+  if (bstat_enabled && p.n_tiles == 1 && (p.a_bytes % 1024) == 0 && (p.b_bytes % 1024) == 0 && b_all <= 64 * 1024) {
+    p.b_stationary = 1;
+    bstat_bytes = b_all;
+    stage = p.a_bytes;
+  }
+  p.num_stages = (kSmemBudget - epi_bytes - bstat_bytes) / (int)stage;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (p.num_stages < 2) p.num_stages = 2;
   p.OH = L.OH; p.OW = L.OW; p.os = L.os; p.oh0 = L.oh0; p.ow0 = L.ow0; p.ldo = L.ldo;
@@ -795,7 +820,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  const int smem_bytes = p.num_stages * (int)stage + epi_bytes + 1024;
+  const int smem_bytes = p.num_stages * (int)stage + bstat_bytes + epi_bytes + 1024;
   rc = set_smem_attr((const void*)conv_igemm_kernel, smem_bytes);
   if (rc) return rc;
   const int total_tiles = p.m_tiles * p.n_tiles;
