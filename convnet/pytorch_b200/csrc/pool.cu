@@ -81,25 +81,32 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // windows containing h: 2p-1 <= h <= 2p+1
-    const int p_lo = h / 2, p_hi = (h + 1) / 2;
-    const int q_lo = w / 2, q_hi = (w + 1) / 2;
-    for (int p = p_lo; p <= p_hi; ++p) {
-      if (p >= OH) continue;
-      const int r = h - (2 * p - 1);
-      for (int q = q_lo; q <= q_hi; ++q) {
-        if (q >= OW) continue;
-        const int s = w - (2 * q - 1);
-        const int want = r * 3 + s;
-        const long long o = (((long long)n * OH + p) * OW + q) * C + v * 8;
-        const uint2 pk = *reinterpret_cast<const uint2*>(amax + o);
-        float g[8];
-        ld8(dy + o, g);
+    // windows containing h: 2p-1 <= h <= 2p+1 (at most 2 x 2 of them); all loads are issued before they are used
+    const int p_lo = h / 2, q_lo = w / 2;
+    uint2 pk[4];
+    uint4 gr[4];
+    int want[4];
+    bool ok[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int b = (i < 4 ? (pk.x >> (8 * i)) : (pk.y >> (8 * (i - 4)))) & 0xff;
-          if (b == want) acc[i] += g[i];
-        }
+    for (int j = 0; j < 4; ++j) {
+      const int p = p_lo + (j >> 1), q = q_lo + (j & 1);
+      ok[j] = p <= (h + 1) / 2 && q <= (w + 1) / 2 && p < OH && q < OW;
+      want[j] = (h - (2 * p - 1)) * 3 + (w - (2 * q - 1));
+      if (ok[j]) {
+        const long long o = (((long long)n * OH + p) * OW + q) * C + v * 8;
+        pk[j] = *reinterpret_cast<const uint2*>(amax + o);
+        gr[j] = *reinterpret_cast<const uint4*>(dy + o);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!ok[j]) continue;
+      const uint32_t gw[4] = {gr[j].x, gr[j].y, gr[j].z, gr[j].w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int b = (i < 4 ? (pk[j].x >> (8 * i)) : (pk[j].y >> (8 * (i - 4)))) & 0xff;
+        const float2 g2 = unpack_bf16x2(gw[i >> 1]);
+        if (b == want[j]) acc[i] += (i & 1) ? g2.y : g2.x;
       }
     }
     st8(dx + (((long long)n * H + h) * W + w) * C + v * 8, acc);

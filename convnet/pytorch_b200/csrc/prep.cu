@@ -66,6 +66,40 @@ __global__ void __launch_bounds__(256) weight_transpose_kernel(const __nv_bfloat
   }
 }
 
+// multi-tensor version: one launch transposes every conv weight of the network (53 launches -> 1 per step).
+// jobs[j] = {src_off, dst_off, K, T, C, tile_start} in elements of the two arenas; a block owns one 32x32 tile and
+// finds its job by binary search over tile_start.
+__global__ void __launch_bounds__(256) weight_transpose_batched_kernel(const __nv_bfloat16* __restrict__ src_base,
+                                                                       __nv_bfloat16* __restrict__ dst_base,
+                                                                       const int* __restrict__ jobs, int njobs) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  int lo = 0, hi = njobs - 1;
+  const int g = blockIdx.x;
+  while (lo < hi) {   // last job with tile_start <= g
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(jobs + mid * 6 + 5) <= g) lo = mid; else hi = mid - 1;
+  }
+  const int* jb = jobs + lo * 6;
+  const __nv_bfloat16* src = src_base + __ldg(jb + 0);
+  __nv_bfloat16* dst = dst_base + __ldg(jb + 1);
+  const int K = __ldg(jb + 2), T = __ldg(jb + 3), C = __ldg(jb + 4);
+  const int local = g - __ldg(jb + 5);
+  const int tiles_c = (C + 31) >> 5, tiles_k = (K + 31) >> 5;
+  const int t = local / (tiles_c * tiles_k);
+  const int rem = local - t * tiles_c * tiles_k;
+  const int k0 = (rem / tiles_c) * 32, c0 = (rem % tiles_c) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, c = c0 + tx;
+    tile[r][tx] = (k < K && c < C) ? src[((long long)k * T + t) * C + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, k = k0 + tx;
+    if (c < C && k < K) dst[((long long)c * T + t) * K + k] = tile[tx][r];
+  }
+}
+
 // stem: w fp32 [K][7][7][C] -> bf16 [K][16][Cpad], tap (ah,aw) in 4x4, channel (bh*2+bw)*C + c,
 // r = 2*ah + bh - 1, s = 2*aw + bw - 1 (out-of-range -> 0)
 __global__ void stem_w_to_s2d_kernel(const float* __restrict__ w, int K, int C, int Cpad,
@@ -151,6 +185,16 @@ extern "C" int b200_weight_transpose(const void* src, void* dst, int K, int T, i
   weight_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, K, T,
                                                                 C);
   B200_CHECK_LAUNCH("weight_transpose_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_weight_transpose_batched(const void* src_base, void* dst_base, const int* jobs, int njobs,
+                                             int total_tiles, b200_stream_t stream) {
+  B200_REQUIRE(src_base && dst_base && jobs && njobs > 0 && total_tiles > 0, B200_ERR_INVALID,
+               "weight_transpose_batched: bad argument");
+  weight_transpose_batched_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src_base, (__nv_bfloat16*)dst_base, jobs, njobs);
+  B200_CHECK_LAUNCH("weight_transpose_batched_kernel");
   return B200_OK;
 }
 

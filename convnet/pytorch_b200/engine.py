@@ -27,6 +27,7 @@ WIDE_STEM = os.environ.get('B200_WIDE_STEM', '1') != '0'  # overlapping-pixel TM
 HALO_STEM = os.environ.get('B200_HALO_STEM', '1') != '0'  # stem fprop on the halo kernel (dense 4x4 description)
 HALO_STEM_WGRAD = os.environ.get('B200_HALO_STEM_WGRAD', '1') != '0'
 WGRAD_STREAM = os.environ.get('B200_WGRAD_STREAM', '1') != '0'   # weight gradients on a second CUDA stream
+BATCHED_TRANSPOSE = os.environ.get('B200_BATCHED_TRANSPOSE', '1') != '0'  # one launch for all dgrad weight layouts
 BN_ACT_MASK = os.environ.get('B200_BN_ACT_MASK', '0') != '0'    # 1-bit activation masks for residual joins (measured: not a win)
 FUSE_BN_STATS = os.environ.get('B200_FUSE_BN_STATS', '1') != '0'  # BN statistics in the conv epilogue
 
@@ -44,6 +45,7 @@ class Arena(object):
 
     def __init__(self, model, device):
         self.device = device
+        self.convs = []          # every engine._Conv built on this arena (batched dgrad-weight transposes)
         slots = []
         seen = set()
         for mod_name, mod in model.named_modules():
@@ -148,6 +150,9 @@ class _Conv(object):
                 or mod.bias is not None:
             raise B200Error('conv %s: only square stride/padding, dilation 1 and bias=False are supported' % s.name)
         self.groups = mod.groups if s.kind == 'conv' else 1
+        self.slot = s
+        self.wt = None           # [C, R*S, K] view of the runtime's transposed shadow (dgrad operand), set by Runtime
+        arena.convs.append(self)
         self.w16 = arena.kernel_view(arena.p16, s)
         self.w32 = arena.kernel_view(arena.p32, s)
         self.g32 = arena.kernel_view(arena.g32, s)
@@ -197,6 +202,27 @@ class Runtime(object):
         self._wg_keep = []
         self.loss_scale_inv = 1.0
         self._build()
+        self._setup_transposes()
+
+    def _setup_transposes(self):
+        """dgrad reads weights as [C][R*S][K]: one batched launch per step transposes the bf16 shadow of every dense
+        (groups == 1) convolution into a second arena; grouped convolutions transpose their expanded weights per
+        unit."""
+        self._p16t, self._wt_jobs, self._wt_tiles = None, None, 0
+        convs = [c for c in self.arena.convs if c.kind == 'conv' and c.groups == 1]
+        if not BATCHED_TRANSPOSE or not convs:
+            return
+        self._p16t = torch.empty_like(self.arena.p16)
+        spec = []
+        for c in convs:
+            off, n = c.slot.offset, c.slot.numel
+            spec.append((off, off, c.K, c.R * c.S, c.C))
+            c.wt = self._p16t[off:off + n].view(c.C, c.R * c.S, c.K)
+        self._wt_jobs, self._wt_tiles = ops.transpose_jobs(spec, self.device)
+
+    def _transpose_weights(self):
+        if self._wt_jobs is not None:
+            ops.weight_transpose_batched(self.arena.p16, self._p16t, self._wt_jobs, self._wt_tiles)
 
     # ---- program construction (overridden per model family) -------------------------------------
     def _build(self):
@@ -309,7 +335,7 @@ class Runtime(object):
             self._wgrad_async(grouped, u.x, dz)
         if not need_dx:
             return None
-        wt = ops.weight_transpose(u.w)
+        wt = conv.wt if (conv.wt is not None and self._wt_jobs is not None) else ops.weight_transpose(u.w)
         return ops.conv_dgrad(dz, wt, u.desc, residual=residual)
 
     # ---- classifier head: global average pool -> (dropout) -> linear as a 1x1 conv on a 1x1 map ----------
@@ -543,6 +569,7 @@ class ResNetRuntime(Runtime):
         return out, tape
 
     def run_backward(self, tape, dlogits):
+        self._transpose_weights()
         d = self._head_bwd(tape['head'], dlogits)
         for spec, saved in zip(reversed(self.blocks), reversed(tape['blocks'])):
             d = self._block_bwd(spec, saved, d)
@@ -654,6 +681,7 @@ class MobileNetRuntime(Runtime):
         return out, tape
 
     def run_backward(self, tape, dlogits):
+        self._transpose_weights()
         d = self._head_bwd(tape['head'], dlogits)
         for spec, units in zip(reversed(self.blocks), reversed(tape['blocks'])):
             skip = d if spec['add_res'] else None   # out = bn(z) + x (no activation): the skip gradient is dy itself

@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200_avgpool_bwd": [_vp, _i, _i, _i, _vp, _vp],
     "b200_input_prep": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "b200_weight_transpose": [_vp, _vp, _i, _i, _i, _vp],
+    "b200_weight_transpose_batched": [_vp, _vp, _vp, _i, _i, _vp],
     "b200_stem_weight_to_s2d": [_vp, _i, _i, _i, _vp, _vp],
     "b200_stem_wgrad_from_s2d": [_vp, _i, _i, _i, _vp, _vp],
     "b200_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],

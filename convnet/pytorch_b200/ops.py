@@ -312,6 +312,25 @@ def weight_transpose(w, out=None):
     return out
 
 
+def transpose_jobs(shapes_and_offsets, device):
+    """[(src_off, dst_off, K, T, C), ...] -> (int32 device tensor [n, 6], total_tiles) for weight_transpose_batched."""
+    rows, tiles = [], 0
+    for src_off, dst_off, K, T, C in shapes_and_offsets:
+        rows.append([src_off, dst_off, K, T, C, tiles])
+        tiles += T * ((K + 31) // 32) * ((C + 31) // 32)
+    return torch.tensor(rows, dtype=torch.int32, device=device), tiles
+
+
+def weight_transpose_batched(src_base, dst_base, jobs, total_tiles):
+    """every job: bf16 [K,T,C] at src_base[src_off:] -> [C,T,K] at dst_base[dst_off:], one launch."""
+    _chk(src_base, bf16, "src_base"); _chk(dst_base, bf16, "dst_base"); _chk(jobs, torch.int32, "jobs")
+    with _T('weight_transpose', 0, 4 * src_base.numel()):
+        _l.check(_l.load().b200_weight_transpose_batched(src_base.data_ptr(), dst_base.data_ptr(), jobs.data_ptr(),
+                                                         int(jobs.shape[0]), int(total_tiles), _stream()),
+                 "b200_weight_transpose_batched")
+    return dst_base
+
+
 def stem_weight_to_s2d(w_f32, K, C, cpad, out):
     _l.check(_l.load().b200_stem_weight_to_s2d(w_f32.data_ptr(), K, C, cpad, out.data_ptr(), _stream()),
              "b200_stem_weight_to_s2d")

@@ -143,6 +143,10 @@ int b200_input_prep(const float* x_nchw, int N, int C, int H, int W, int Cpad, i
 /* bf16 [K][T][C] -> bf16 [C][T][K] (dgrad weight layout), multi-tensor: n tensors described by
  * device arrays. */
 int b200_weight_transpose(const void* src, void* dst, int K, int T, int C, b200_stream_t stream);
+/* all conv weights of a network in one launch: jobs (device) = njobs x {src_off, dst_off, K, T, C, tile_start} ints,
+ * offsets in elements from src_base / dst_base, tile_start = running sum of T*ceil(K/32)*ceil(C/32) */
+int b200_weight_transpose_batched(const void* src_base, void* dst_base, const int* jobs, int njobs, int total_tiles,
+                                  b200_stream_t stream);
 /* 7x7/s2/p3 stem weights fp32 [K][7][7][C] -> s2d bf16 [K][4*4][Cpad] and the reverse for wgrad */
 int b200_stem_weight_to_s2d(const float* w, int K, int C, int Cpad, void* w_s2d, b200_stream_t stream);
 int b200_stem_wgrad_from_s2d(const float* dw_s2d, int K, int C, int Cpad, float* dw, b200_stream_t stream);

@@ -197,6 +197,19 @@ def test_weight_transpose_and_cast():
     dst = torch.empty(100003, device='cuda', dtype=bf16)
     ops.cast_bf16(src, dst)
     assert torch.equal(dst, src.to(bf16))
+    # multi-tensor transpose: three weights of different shapes inside one flat arena, one launch
+    shapes = [(70, 9, 40), (64, 1, 256), (33, 4, 16)]
+    offs, n = [], 0
+    for K, T, C in shapes:
+        offs.append(n)
+        n += (K * T * C + 63) // 64 * 64
+    flat = torch.randn(n).cuda().to(bf16)
+    out = torch.zeros_like(flat)
+    jobs, tiles = ops.transpose_jobs([(o, o, K, T, C) for o, (K, T, C) in zip(offs, shapes)], 'cuda')
+    ops.weight_transpose_batched(flat, out, jobs, tiles)
+    for o, (K, T, C) in zip(offs, shapes):
+        want = flat[o:o + K * T * C].view(K, T, C).permute(2, 1, 0).contiguous()
+        assert torch.equal(out[o:o + K * T * C].view(C, T, K), want)
 
 
 @pytest.mark.parametrize("B,K,ld,eps", [(64, 1000, 1000, 0.0), (37, 10, 16, 0.0), (64, 1000, 1000, 0.1)])
