@@ -6,9 +6,12 @@
 // (row_in_iter = t / cv, vec = t % cv) with cv = C/8 channel vectors, so every iteration of a block touches
 // one contiguous span of memory and per-channel coefficients are loaded once per thread.
 //
-// Reductions are single-kernel: per-block partial sums (registers -> shared) are added into fp64 accumulators
-// in the workspace with atomicAdd(double); the last block to finish (ticket counter) finalises and re-zeroes
-// the workspace.  The workspace must be zero before first use and must not be shared by concurrent streams.
+// Forward statistics normally come from the convolution epilogue (fp64 atomics into 16 replica rows of the
+// workspace, finished by bn_finalize_kernel); bn_stats_kernel is the stand-alone version for outputs the conv kernel
+// cannot cover (single kernel: the last block, elected by a ticket counter, finalises and re-zeroes the
+// accumulators).  The backward reduction writes one partial row per block and a second tiny kernel sums them in a
+// fixed order (no atomics: same-address fp64 atomics at the end of ~600 blocks cost more than the extra launch).
+// The workspace must be zero before first use and must not be shared by concurrent streams.
 #include "common.cuh"
 #include "host.h"
 #include <stdlib.h>
@@ -349,32 +352,6 @@ __device__ __forceinline__ void loadfv(const float* p, float (&f)[VEC]) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p + i));
     f[i] = a.x; f[i + 1] = a.y; f[i + 2] = a.z; f[i + 3] = a.w;
   }
-}
-
-// Block partials (VEC channels x 2 statistics per thread) -> fp64 global accumulators; true in the LAST block.
-template <int VEC>
-__device__ __forceinline__ bool accumulate_and_elect_v(float (&acc)[2 * VEC], int cv, int rows_per_iter, int C,
-                                                       double* accum, unsigned* ticket) {
-  __shared__ float red[kBnThreads][2 * VEC + 1];
-  __shared__ bool is_last;
-  const int t = threadIdx.x;
-#pragma unroll
-  for (int i = 0; i < 2 * VEC; ++i) red[t][i] = acc[i];
-  __syncthreads();
-  for (int o = t; o < 2 * C; o += kBnThreads) {
-    const int stat = o / C;
-    const int c = o - stat * C;
-    const int v = c / VEC, e = c - v * VEC;
-    float s = 0.f;
-    for (int r = 0; r < rows_per_iter; ++r) s += red[r * cv + v][stat * VEC + e];
-    atomicAdd(accum + (blockIdx.x % kReplicas) * 2 * C + o, (double)s);
-  }
-  __threadfence();
-  __syncthreads();
-  if (t == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (is_last) __threadfence();
-  return is_last;
 }
 
 // ---- backward reduce: dbeta = sum g, dgamma = sum g * xhat ------------------------------------------

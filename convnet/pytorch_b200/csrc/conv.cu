@@ -856,10 +856,10 @@ extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const voi
   B200_REQUIRE(x && w && y, B200_ERR_INVALID, "conv_fprop: null pointer");
   B200_REQUIRE(d->C % 8 == 0, B200_ERR_UNSUPPORTED, "conv_fprop: C=%d must be a multiple of 8 (pad the input)", d->C);
   if (d->stride == 1 && d->pad_h == d->pad_w && d->P == d->H + 2 * d->pad_h - d->R + 1 &&
-      d->Q == d->W + 2 * d->pad_w - d->S + 1 && d->x_pixel_stride == 0 && (!ep || (!ep->bias && !ep->out_fp32)) &&
-      halo_eligible(d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h)) {
-    return launch_halo(x, w, y, ep ? ep->residual : nullptr, d->N, d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h, 0,
-                       ep ? ep->act : 0,
+      d->Q == d->W + 2 * d->pad_w - d->S + 1 && d->x_pixel_stride == 0 && (!ep || !ep->out_fp32) &&
+      !(ep && ep->bias && ep->bn_stats_workspace) && halo_eligible(d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h)) {
+    return launch_halo(x, w, y, ep ? ep->residual : nullptr, ep ? ep->bias : nullptr, d->N, d->P, d->Q, d->C, d->K,
+                       d->R, d->S, d->pad_h, 0, ep ? ep->act : 0,
                        (ep && ep->bn_stats_workspace) ? reinterpret_cast<double*>(ep->bn_stats_workspace) : nullptr,
                        (cudaStream_t)stream);
   }
@@ -895,7 +895,7 @@ extern "C" int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const vo
   B200_REQUIRE(st == 1 || st == 2, B200_ERR_UNSUPPORTED, "conv_dgrad: stride %d unsupported", st);
   if (d->R == 3 && d->S == 3 && st == 1 && d->pad_h == 1 && d->pad_w == 1 && d->P == d->H && d->Q == d->W &&
       halo_eligible(d->H, d->W, d->K, d->C, 3, 3, 1)) {
-    return launch_halo(dy, wt, dx, residual, d->N, d->H, d->W, d->K, d->C, 3, 3, 1, 1, 0, nullptr, stream);
+    return launch_halo(dy, wt, dx, residual, nullptr, d->N, d->H, d->W, d->K, d->C, 3, 3, 1, 1, 0, nullptr, stream);
   }
   // dx[h,w] = sum_{r,s : (h+pad-r) % st == 0} dy[(h+pad-r)/st, (w+pad-s)/st] * w[r,s]
   // one launch per residue class (h % st, w % st); each class is a stride-1 correlation over dy.

@@ -36,6 +36,7 @@ struct HaloParams {
   int act;
   int has_res;
   double* stats;
+  const float* bias;       // [Kout] fp32 added before the residual / activation (BN folded for inference), or nullptr
   int ntaps, pad;
   int row_bytes;           // bytes of one source pixel chunk: 128 (64 channels) or 32 (16 channels)
   int b_stationary;        // 1: all c_chunks*ntaps weight slices of the n-tile stay in shared memory
@@ -207,6 +208,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(vv[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + nbase + c0 + i);
+          }
           uint8_t* row = epi + (c0 >> 6) * box_pitch + srow * 128;
           const int j0 = (c0 & 63) >> 3;
           uint4* p0 = reinterpret_cast<uint4*>(row + ((j0 ^ (srow & 7)) << 4));
@@ -322,8 +327,8 @@ bool halo_eligible(int H, int W, int Cs, int Nout, int R, int S, int pad) {
 }
 
 // dir 0: fprop (tap (r,s) reads halo offset (r,s), weight slice r*S+s); dir 1: dgrad (offset (R-1-r, S-1-s))
-int launch_halo(const void* src, const void* wmat, void* out, const void* res, int N, int H, int W, int Cs, int Nout,
-                int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream) {
+int launch_halo(const void* src, const void* wmat, void* out, const void* res, const float* bias, int N, int H, int W,
+                int Cs, int Nout, int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream) {
   HaloParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W; p.C = Cs; p.Kout = Nout;
@@ -346,6 +351,7 @@ int launch_halo(const void* src, const void* wmat, void* out, const void* res, i
   p.act = act;
   p.has_res = res != nullptr;
   p.stats = stats;
+  p.bias = bias;
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) {
       const int t = r * S + s;

@@ -27,8 +27,8 @@ EncodeIm2colFn encode_im2col_fn();
 // H, W are the OUTPUT map dimensions.
 bool halo_geometry_ok(int H, int W, int Cs, int R, int S, int pad);
 bool halo_eligible(int H, int W, int Cs, int Nout, int R, int S, int pad);
-int launch_halo(const void* src, const void* wmat, void* out, const void* res, int N, int H, int W, int Cs, int Nout,
-                int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream);
+int launch_halo(const void* src, const void* wmat, void* out, const void* res, const float* bias, int N, int H, int W,
+                int Cs, int Nout, int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream);
 
 bool halo_wgrad_eligible(int H, int W, int C, int K_out, int R, int S, int pad);
 int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t workspace_bytes, int N, int H,

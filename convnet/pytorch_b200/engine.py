@@ -27,6 +27,7 @@ WIDE_STEM = os.environ.get('B200_WIDE_STEM', '1') != '0'  # overlapping-pixel TM
 HALO_STEM = os.environ.get('B200_HALO_STEM', '1') != '0'  # stem fprop on the halo kernel (dense 4x4 description)
 HALO_STEM_WGRAD = os.environ.get('B200_HALO_STEM_WGRAD', '1') != '0'
 WGRAD_STREAM = os.environ.get('B200_WGRAD_STREAM', '1') != '0'   # weight gradients on a second CUDA stream
+FOLD_BN_EVAL = os.environ.get('B200_FOLD_BN_EVAL', '1') != '0'   # inference: BN folded into conv weights + epilogue bias
 BATCHED_TRANSPOSE = os.environ.get('B200_BATCHED_TRANSPOSE', '1') != '0'  # one launch for all dgrad weight layouts
 BN_ACT_MASK = os.environ.get('B200_BN_ACT_MASK', '0') != '0'    # 1-bit activation masks for residual joins (measured: not a win)
 FUSE_BN_STATS = os.environ.get('B200_FUSE_BN_STATS', '1') != '0'  # BN statistics in the conv epilogue
@@ -46,6 +47,7 @@ class Arena(object):
     def __init__(self, model, device):
         self.device = device
         self.convs = []          # every engine._Conv built on this arena (batched dgrad-weight transposes)
+        self.version = 0         # bumped whenever parameters or BN running statistics may have changed
         slots = []
         seen = set()
         for mod_name, mod in model.named_modules():
@@ -127,6 +129,7 @@ class Arena(object):
     def sync_shadow(self):
         """bf16 shadow <- fp32 master (whole arena, one kernel)."""
         ops.cast_bf16(self.p32, self.p16)
+        self.version += 1
 
     def zero_grad(self):
         self.g32.zero_()
@@ -200,6 +203,8 @@ class Runtime(object):
         self._ws = torch.zeros(ops.bn_workspace_floats(self._max_c), device=device, dtype=torch.float32)
         self._wg_stream = torch.cuda.Stream(device=device) if WGRAD_STREAM else None
         self._wg_keep = []
+        self._fold_cache = {}
+        self._want_tape = True
         self.loss_scale_inv = 1.0
         self._build()
         self._setup_transposes()
@@ -232,9 +237,44 @@ class Runtime(object):
     def _coeffs(self, n):
         return torch.empty(n, device=self.device, dtype=torch.float32)
 
+    # ---- inference: BatchNorm folded into the convolution (reference utils/absorb_bn.py:18-48) ----------------
+    # w' = w * gamma/sqrt(var+eps) per output channel, b' = beta - mean*gamma/sqrt(var+eps): one kernel computes
+    # act(conv(x, w') + b' [+ residual]) -- no z tensor, no separate BN pass.  Folded weights are cached until the
+    # parameters or the running statistics change (arena.version).
+    def _folded(self, conv, bn):
+        key = (id(conv), id(bn))
+        hit = self._fold_cache.get(key)
+        if hit is not None and hit[0] == self.arena.version:
+            return hit[1], hit[2]
+        m = bn.mod
+        coef = self._coeffs(2 * bn.C)
+        scale, shift = coef[:bn.C], coef[bn.C:]
+        ops.bn_eval_coeffs(bn.gamma, bn.beta, m.running_mean, m.running_var, m.eps, scale, shift)
+        w32 = conv.w32 * scale.view(-1, 1, 1)                      # [K, T, C/g] fp32, once per version (not per step)
+        if conv.groups == 1:
+            wf = w32.to(torch.bfloat16).contiguous()
+        else:
+            wf = ops.group_weight_expand(w32.contiguous(), conv.K, conv.R * conv.S, conv.C, conv.groups)
+        self._fold_cache[key] = (self.arena.version, wf, shift)
+        return wf, shift
+
+    def _unit_fwd_folded(self, x, conv, bn, act, residual=None, other=None):
+        N, H, W, _ = x.shape
+        u = _Unit()
+        u.conv, u.bn, u.act, u.x = conv, bn, act, x
+        u.desc = conv.desc(N, H, W)
+        wf, bf = self._folded(conv, bn)
+        if other is not None:                # downsample branch: r = conv_ds'(x_block) + b_ds', added below
+            residual = other.y
+        u.z, u.mask = None, None
+        u.y = ops.conv_fprop(x, wf, u.desc, bias=bf, residual=residual, act=act)
+        return u
+
     def _unit_fwd(self, x, conv, bn, act, training, tape, residual=None, other=None):
         """z = conv(x); BN statistics (train) / running-stat coefficients (eval);
         y = act(bn(z) + residual | + bn_other(z_other)).  Returns y and (if tape) the saved unit."""
+        if not training and FOLD_BN_EVAL and not self._want_tape:
+            return self._unit_fwd_folded(x, conv, bn, act, residual=residual, other=other)
         N, H, W, _ = x.shape
         u = _Unit()
         u.conv, u.bn, u.act, u.x = conv, bn, act, x
@@ -281,6 +321,8 @@ class Runtime(object):
 
     def _stats_only(self, x, conv, bn, training):
         """conv + BN coefficients without the apply (used for the downsample branch, fused into the main apply)."""
+        if not training and FOLD_BN_EVAL and not self._want_tape:
+            return self._unit_fwd_folded(x, conv, bn, ACT_NONE)       # y = bn_ds(conv_ds(x)) in one kernel
         N, H, W, _ = x.shape
         u = _Unit()
         u.conv, u.bn, u.act, u.x = conv, bn, ACT_NONE, x
@@ -559,6 +601,9 @@ class ResNetRuntime(Runtime):
 
     # ---- whole network ------------------------------------------------------------------------------
     def run_forward(self, x, training, want_tape):
+        self._want_tape = want_tape
+        if training:
+            self.arena.version += 1          # running statistics change: folded inference weights become stale
         h, stem = self._stem_fwd(x, training)
         saved = []
         for spec in self.blocks:
@@ -665,6 +710,9 @@ class MobileNetRuntime(Runtime):
         self._wgrad_async(stem_wgrad, u.x, dz)
 
     def run_forward(self, x, training, want_tape):
+        self._want_tape = want_tape
+        if training:
+            self.arena.version += 1
         h, stem = self._stem_fwd(x, training)
         saved = []
         for spec in self.blocks:

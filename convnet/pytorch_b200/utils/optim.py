@@ -143,6 +143,7 @@ class B200SGD(torch.optim.Optimizer):
         first = not self._have_momentum
         ops.fused_sgd(arena.p32, arena.g32, self.m32, arena.p16, arena.total, wd_count, g['lr'], g['momentum'],
                       g['dampening'], wd_val, self.inv_scale, self.coef_dev, first)
+        arena.version += 1       # folded inference weights / transposed shadows derived from p16 are stale
         if g['momentum'] != 0 and first:
             self._have_momentum = True
             self._bind_state()

@@ -306,3 +306,41 @@ def test_trainer_cuda_graph_replay_matches_eager():
     assert abs(r0['loss'] - r1['loss']) < 2e-3 * max(1.0, abs(r0['loss']))
     for k in s0:
         assert _rel(s1[k], s0[k]) < 2e-3, '%s: %.3e' % (k, _rel(s1[k], s0[k]))
+
+
+@pytest.mark.parametrize("family", ["resnet50", "resnext50"])
+def test_eval_with_folded_batchnorm(family):
+    """Inference path: BN folded into the conv weights + epilogue bias (utils/absorb_bn.py:18-48 of the reference)
+    must agree with the unfolded kernels and with stock torch eval; the folded-weight cache must follow parameter
+    and running-statistics updates."""
+    from convnet.pytorch_b200 import engine
+    from convnet.pytorch_b200.models import resnet, resnext
+    factory = resnet if family == "resnet50" else resnext
+    ref, mine, x, y = _pair(factory, dict(dataset='imagenet', depth=50), (3, 64, 64), 1000, steps=3, batch=8)
+    saved = engine.FOLD_BN_EVAL
+    try:
+        ref.eval(); mine.eval()
+        with torch.no_grad():
+            engine.FOLD_BN_EVAL = False
+            a0 = mine(x)
+            engine.FOLD_BN_EVAL = True
+            a1 = mine(x)
+            a2 = mine(x)                      # second call: cached folded weights
+            b = ref(x.to(torch.bfloat16).float())
+        assert torch.equal(a1, a2)
+        assert _rel(a1, a0) < 2e-2, 'folded vs unfolded %.3e' % _rel(a1, a0)
+        assert _rel(a1, b) < 3e-2, 'folded vs torch eval %.3e' % _rel(a1, b)
+        # one training forward/backward moves the running statistics: the cache must be rebuilt
+        mine.train()
+        mine._b200.arena.zero_grad()
+        F.cross_entropy(mine(x), y).backward()
+        mine.eval()
+        with torch.no_grad():
+            engine.FOLD_BN_EVAL = False
+            c0 = mine(x)
+            engine.FOLD_BN_EVAL = True
+            c1 = mine(x)
+        assert _rel(c1, c0) < 2e-2, 'after update: folded vs unfolded %.3e' % _rel(c1, c0)
+        assert _rel(c1, a1) > 1e-4, 'folded weights were not refreshed after the running statistics changed'
+    finally:
+        engine.FOLD_BN_EVAL = saved
