@@ -148,3 +148,20 @@ def test_data_parallel_world2_gloo():
     mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret['same'], 'parameters diverged across ranks'
     assert ret['sum'], 'flat-arena all-reduce / folded 1/world factor wrong'
+
+
+def test_cli_cpu_plumbing_run(tmp_path):
+    """BASELINE config C1 through the reference-compatible CLI (main.py:28-360 of the reference): resnet depth 20 on
+    synthetic CIFAR-10, CPU, stock torch layers: train -> validate -> checkpoint -> results.csv."""
+    from convnet.pytorch_b200 import main as cli
+    cli.main(['--model', 'resnet', '--model-config', "{'depth': 20}", '--dataset', 'synthetic_cifar10',
+              '--device', 'cpu', '-b', '16', '--epochs', '1', '--max-steps', '3', '--workers', '0',
+              '--results-dir', str(tmp_path), '--save', 'cli_cpu'])
+    out = tmp_path / 'cli_cpu'
+    for name in ('checkpoint.pth.tar', 'model_best.pth.tar', 'results.csv', 'config.json', 'log.txt'):
+        assert (out / name).exists(), name
+    import csv
+    rows = list(csv.DictReader(open(out / 'results.csv')))
+    assert len(rows) == 1 and float(rows[0]['training loss']) > 0 and 0 <= float(rows[0]['validation prec1']) <= 100
+    ck = torch.load(out / 'checkpoint.pth.tar', map_location='cpu', weights_only=False)
+    assert ck['epoch'] == 1 and 'state_dict' in ck and any(k.endswith('conv1.weight') for k in ck['state_dict'])
