@@ -863,6 +863,14 @@ extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const voi
                        (ep && ep->bn_stats_workspace) ? reinterpret_cast<double*>(ep->bn_stats_workspace) : nullptr,
                        (cudaStream_t)stream);
   }
+  if (d->R == 1 && d->S == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && d->x_pixel_stride == 0 &&
+      (!ep || !ep->out_fp32) && !(ep && ep->bias && ep->bn_stats_workspace) &&
+      pair_eligible((long long)d->N * d->H * d->W, d->C, d->K)) {   // opt-in CTA-pair kernel (conv_pair.cu)
+    return launch_pair(x, w, y, ep ? ep->residual : nullptr, ep ? ep->bias : nullptr, (long long)d->N * d->H * d->W, d->C,
+                       d->K, ep ? ep->act : 0,
+                       (ep && ep->bn_stats_workspace) ? reinterpret_cast<double*>(ep->bn_stats_workspace) : nullptr,
+                       (cudaStream_t)stream);
+  }
   IgemmLaunch L;
   memset(&L, 0, sizeof(L));
   L.src = x; L.Nimg = d->N; L.SH = d->H; L.SW = d->W; L.SC = d->C;
@@ -896,6 +904,10 @@ extern "C" int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const vo
   if (d->R == 3 && d->S == 3 && st == 1 && d->pad_h == 1 && d->pad_w == 1 && d->P == d->H && d->Q == d->W &&
       halo_eligible(d->H, d->W, d->K, d->C, 3, 3, 1)) {
     return launch_halo(dy, wt, dx, residual, nullptr, d->N, d->H, d->W, d->K, d->C, 3, 3, 1, 1, 0, nullptr, stream);
+  }
+  if (d->R == 1 && d->S == 1 && st == 1 && d->pad_h == 0 && d->pad_w == 0 &&
+      pair_eligible((long long)d->N * d->H * d->W, d->K, d->C)) {   // opt-in CTA-pair kernel: dx = dy * wt^T
+    return launch_pair(dy, wt, dx, residual, nullptr, (long long)d->N * d->H * d->W, d->K, d->C, 0, nullptr, stream);
   }
   // dx[h,w] = sum_{r,s : (h+pad-r) % st == 0} dy[(h+pad-r)/st, (w+pad-s)/st] * w[r,s]
   // one launch per residue class (h % st, w % st); each class is a stride-1 correlation over dy.

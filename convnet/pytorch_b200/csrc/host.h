@@ -34,6 +34,11 @@ bool halo_wgrad_eligible(int H, int W, int C, int K_out, int R, int S, int pad);
 int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t workspace_bytes, int N, int H,
                       int W, int C, int K_out, int R, int S, int pad, cudaStream_t stream);
 
+// conv_pair.cu: EXPERIMENTAL cta_group::2 GEMM for wide 1x1 / stride-1 layers (B200_IGEMM_PAIR=1)
+bool pair_eligible(long long M, int C, int Nout);
+int launch_pair(const void* a, const void* w, void* out, const void* res, const float* bias, long long M, int C, int Nout,
+                int act, double* stats, cudaStream_t stream);
+
 // warps of a split-K reduce block that share the loop over the splits (1..8)
 int wgrad_reduce_warps(int splits);
 
