@@ -380,7 +380,6 @@ _CONV_CASE_NAMES = [
     # halo (shift-GEMM) path: 3x3 stride 1 at several map sizes / ragged last tile / residual epilogue / stem 4x4
     'halo_28_128', 'halo_14_256', 'halo_56_res', 'halo_36_odd', 'halo_18_512', 'halo_20x12', 'halo_56_128',
     'halo_8_256', 'halo_stem', 'halo_stem_67',
-    'p1_256_128_ragged', 'p1_512_512_res', 'p1_256_1024_14',
 ]
 
 
