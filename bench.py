@@ -246,12 +246,16 @@ def main():
         sync_all()
         n_e2e = max(10, args.steps)
         # raw pinned-host -> device bandwidth of this box (explains e2e when PCIe, not the GPU, is the bound)
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        h0.record()
-        x_host.to(dev, non_blocking=True)
-        h1.record()
-        torch.cuda.synchronize()
-        h2d_ms = h0.elapsed_time(h1)
+        h2d_ms = float('inf')
+        x_probe = torch.empty_like(x_dev)
+        for _ in range(3):            # best of 3 into a preallocated buffer (the first copy pays one-off set-up)
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            x_probe.copy_(x_host, non_blocking=True)
+            h1.record()
+            torch.cuda.synchronize()
+            h2d_ms = min(h2d_ms, h0.elapsed_time(h1))
+        del x_probe
         loader = [(x_host, y_host)] * n_e2e
         windows = []
         for _ in range(2):    # two windows of n_e2e steps; the first one still pays one-off allocator / replay warm-up
@@ -289,7 +293,9 @@ def main():
         hbm_names = [n for n in classes if not n.startswith('conv_') and n != 'allreduce_nccl']
         hbm_ms = sum(classes[n]['ms'] for n in hbm_names)
         hbm_bytes = sum(classes[n]['bytes'] for n in hbm_names)
-        dom = max(classes, key=lambda n: classes[n]['ms'])
+        # the gradient all-reduce is not one of this library's kernels and its first eager call is not steady state:
+        # it is reported under 'classes' but never picked as the dominant kernel
+        dom = max((n for n in classes if n != 'allreduce_nccl'), key=lambda n: classes[n]['ms'])
         d = classes[dom]
         if dom.startswith('conv_'):
             ach = d['flops'] / (d['ms'] * 1e-3) / 1e12 / max(d['calls'], 1) * d['calls']

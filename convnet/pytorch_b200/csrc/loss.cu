@@ -28,7 +28,8 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
 __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __restrict__ logits,
                                                                 const long long* __restrict__ target, int B,
                                                                 int classes, int ld, float eps, float grad_scale,
-                                                                float* __restrict__ loss,
+                                                                const float* __restrict__ grad_scale_dev,
+                                                                float* __restrict__ row_loss,
                                                                 __nv_bfloat16* __restrict__ dlogits) {
   __shared__ float sh[kCeThreads / 32];
   const int b = blockIdx.x;
@@ -48,13 +49,12 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __r
   const int t = (int)target[b];
   const float eps_sum = eps / (float)classes;
   const float eps_nll = 1.f - eps_sum - eps;
-  if (threadIdx.x == 0) {
+  if (row_loss != nullptr && threadIdx.x == 0) {
     // sum_c lsm[c] = sx - classes*lse
-    const float li = -(eps_nll * (row[t] - lse) + eps_sum * (sx - (float)classes * lse));
-    atomicAdd(loss, li / (float)B);
+    row_loss[b] = -(eps_nll * (row[t] - lse) + eps_sum * (sx - (float)classes * lse));
   }
   if (dlogits != nullptr) {
-    const float gs = grad_scale / (float)B;
+    const float gs = grad_scale * (grad_scale_dev != nullptr ? __ldg(grad_scale_dev) : 1.f) / (float)B;
     // d/dx_c of li: (eps_nll + classes*eps_sum) * softmax_c - eps_nll*[c==t] - eps_sum
     const float wsm = eps_nll + (float)classes * eps_sum;
     for (int c = threadIdx.x; c < classes; c += kCeThreads) {
@@ -64,6 +64,16 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __r
     }
     for (int c = classes + threadIdx.x; c < ld; c += kCeThreads) dlogits[(long long)b * ld + c] = __float2bfloat16(0.f);
   }
+}
+
+// loss = mean_b row_loss[b]: one block, fixed summation order (bit-reproducible, no atomics, no pre-zeroed output)
+__global__ void __launch_bounds__(kCeThreads) ce_mean_kernel(const float* __restrict__ row_loss, int B,
+                                                             float* __restrict__ loss) {
+  __shared__ float sh[kCeThreads / 32];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += kCeThreads) s += row_loss[b];
+  s = block_reduce(s, false, sh);
+  if (threadIdx.x == 0) *loss = s / (float)B;
 }
 
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ m, int B, int K,
@@ -80,13 +90,20 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 using namespace b200;
 
 extern "C" int b200_softmax_ce(const float* logits, const long long* target, int B, int classes, int ld,
-                               float smooth_eps,
-                               float grad_scale, float* loss, void* dlogits_bf16, b200_stream_t stream) {
-  B200_REQUIRE(logits && target && loss && B > 0 && classes > 0 && ld >= classes, B200_ERR_INVALID,
+                               float smooth_eps, float grad_scale, const float* grad_scale_dev, float* loss,
+                               float* row_loss, void* dlogits_bf16, b200_stream_t stream) {
+  B200_REQUIRE(logits && target && B > 0 && classes > 0 && ld >= classes, B200_ERR_INVALID,
                "softmax_ce: bad argument");
+  B200_REQUIRE((loss == nullptr) == (row_loss == nullptr), B200_ERR_INVALID,
+               "softmax_ce: loss and row_loss must be given together");
+  B200_REQUIRE(loss != nullptr || dlogits_bf16 != nullptr, B200_ERR_INVALID, "softmax_ce: nothing to compute");
   softmax_ce_kernel<<<B, kCeThreads, 0, (cudaStream_t)stream>>>(logits, target, B, classes, ld, smooth_eps, grad_scale,
-                                                              loss, (__nv_bfloat16*)dlogits_bf16);
+                                                              grad_scale_dev, row_loss, (__nv_bfloat16*)dlogits_bf16);
   B200_CHECK_LAUNCH("softmax_ce_kernel");
+  if (loss != nullptr) {
+    ce_mean_kernel<<<1, kCeThreads, 0, (cudaStream_t)stream>>>(row_loss, B, loss);
+    B200_CHECK_LAUNCH("ce_mean_kernel");
+  }
   return B200_OK;
 }
 

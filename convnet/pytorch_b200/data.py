@@ -46,6 +46,51 @@ class SyntheticImages(Dataset):
         return img, int(self.labels[idx])
 
 
+_IMAGE_STATS = {'mean': [0.485, 0.456, 0.406], 'std': [0.229, 0.224, 0.225]}   # preprocess.py:7-8 of the reference
+
+
+def real_dataset_transform(transform_name='imagenet', input_size=None, scale_size=None, normalize=None, augment=True,
+                           cutout=None, autoaugment=False, padding=None, duplicates=1, num_crops=1):
+    """The basic transform stacks the reference's ``get_transform`` selects for real image datasets
+    (preprocess.py:114-161): random-resized-crop + flip (imagenet, train), pad-4 random crop + flip (cifar, train),
+    resize + centre crop (evaluation), then ToTensor + Normalize.  The research augmentations -- AutoAugment, Cutout,
+    Lighting/colour jitter, multi-crop evaluation -- are outside this repo's scope
+    and raise instead of being silently dropped."""
+    import torchvision.transforms as T
+    if autoaugment or cutout is not None or num_crops != 1:
+        raise NotImplementedError('autoaugment / cutout / multi-crop evaluation are outside the B200 hot path '
+                                  '(reference preprocess.py, autoaugment.py); use the reference data pipeline')
+    stats = normalize or _IMAGE_STATS
+    tail = [T.ToTensor(), T.Normalize(**stats)]
+    if 'imagenet' in transform_name:
+        input_size = input_size or 224
+        scale_size = scale_size or int(input_size * 8 / 7)
+        if augment:
+            # the reference's inception_preprocess adds ColorJitter + PCA Lighting (preprocess.py:77-97) which are not
+            # reproduced: say so rather than train on a silently different distribution
+            import logging
+            logging.warning('imagenet training transform: RandomResizedCrop + flip only (no colour jitter / lighting)')
+            head = [T.RandomResizedCrop(input_size), T.RandomHorizontalFlip()]
+        else:
+            head = ([T.Resize(scale_size)] if scale_size != input_size else []) + [T.CenterCrop(input_size)]
+    elif 'cifar' in transform_name:
+        input_size = input_size or 32
+        scale_size = scale_size or 32
+        if augment:
+            head = [T.RandomCrop(scale_size, padding=padding or 4)]
+            if input_size != scale_size:
+                head.append(T.Resize(input_size))
+            head.append(T.RandomHorizontalFlip())
+        else:
+            head = ([T.Resize(scale_size)] if scale_size != input_size else []) + [T.CenterCrop(input_size)]
+    else:
+        raise NotImplementedError('no transform for dataset family %r' % transform_name)
+    fn = T.Compose(head + tail)
+    if duplicates > 1:   # batch augmentation: D independent draws of the transform per sample (preprocess.py:105-112)
+        return T.Lambda(lambda img: torch.stack([fn(img) for _ in range(duplicates)], dim=0))
+    return fn
+
+
 _SYNTHETIC = {'synthetic_cifar10': (32, 10, 50000, 10000), 'synthetic_cifar100': (32, 100, 50000, 10000),
               'synthetic_imagenet': (224, 1000, 1281167, 50000)}
 
@@ -115,6 +160,11 @@ class DataRegime(object):
             if name in _SYNTHETIC:  # the "transform" of a synthetic dataset is just its geometry
                 data_kwargs['input_size'] = setting['transform'].get('input_size')
                 data_kwargs['duplicates'] = setting['transform'].get('duplicates') or 1
+            elif data_kwargs.get('transform') is None:
+                # real images: build the transform the regime asks for (reference data.py:101-102) -- never fall back
+                # to a bare ToTensor(), which would train on unnormalised, unaugmented, variable-size images
+                tf = {k: v for k, v in setting['transform'].items() if v is not None}
+                data_kwargs['transform'] = real_dataset_transform(**tf)
             self._data = get_dataset(**data_kwargs)
             if subset_indices is not None:
                 self._data = Subset(self._data, subset_indices)

@@ -48,6 +48,7 @@ class Arena(object):
         self.device = device
         self.convs = []          # every engine._Conv built on this arena (batched dgrad-weight transposes)
         self.version = 0         # bumped whenever parameters or BN running statistics may have changed
+        self.grads_zero = False  # True while g32 is known to be all zeros (the fused SGD kernel cleared it in its pass)
         slots = []
         seen = set()
         for mod_name, mod in model.named_modules():
@@ -132,7 +133,11 @@ class Arena(object):
         self.version += 1
 
     def zero_grad(self):
-        self.g32.zero_()
+        """g32 <- 0.  A no-op when the fused SGD kernel already cleared the arena while consuming the gradients
+        (B200SGD.fold_zero_grad) and nothing has been accumulated since."""
+        if not self.grads_zero:
+            self.g32.zero_()
+            self.grads_zero = True
 
     def rebind_grads(self):
         for s in self.slots:
@@ -161,7 +166,8 @@ class _Conv(object):
         self.g32 = arena.kernel_view(arena.g32, s)
 
     def desc(self, N, H, W):
-        return ops.make_desc(N, H, W, self.C, self.K, self.R, self.S, self.stride, self.pad)
+        return ops.make_desc(N, H, W, self.C, self.K, self.R, self.S, self.stride, self.pad,
+                             algo_macs=self.K * self.R * self.S * self.C // self.groups)
 
     def kernel_weights(self):
         """bf16 [K, R*S, C] operand of the dense kernels: the arena shadow, or for a grouped convolution the
@@ -206,6 +212,8 @@ class Runtime(object):
         self._fold_cache = {}
         self._want_tape = True
         self.loss_scale_inv = 1.0
+        self._fused_dl = None        # bf16 dlogits handed from _FusedCE.backward to run_backward (side channel)
+        self._ce_dummy = torch.zeros((), device=device, dtype=torch.float32)
         self._build()
         self._setup_transposes()
 
@@ -402,15 +410,18 @@ class Runtime(object):
             keep = 1.0 - self.dropout_p
             mask = (torch.rand(feat.shape, device=self.device) < keep).to(torch.bfloat16) / keep
             feat = feat * mask
-        desc = ops.make_desc(N, 1, 1, self.fc_in, self.classes_pad, 1, 1, 1, 0)
+        desc = ops.make_desc(N, 1, 1, self.fc_in, self.classes_pad, 1, 1, 1, 0, algo_macs=self.fc_in * self.classes)
         logits = ops.conv_fprop(feat, self.fc_w16, desc, bias=self.fc_b, out_fp32=True).view(N, self.classes_pad)
         out = logits if self.classes_pad == self.classes else logits[:, :self.classes]
-        tape = {'feat': feat, 'mask': mask, 'last_shape': tuple(h.shape), 'fc_desc': desc} if want_tape else None
+        tape = {'feat': feat, 'mask': mask, 'last_shape': tuple(h.shape), 'fc_desc': desc,
+                'logits_pad': logits} if want_tape else None
         return out, tape
 
-    def _head_bwd(self, tape, dlogits):
+    def _head_bwd(self, tape, dlogits, dl_bf16=None):
         N = dlogits.shape[0]
-        if self.classes_pad == self.classes:
+        if dl_bf16 is not None:              # written by the fused softmax-CE kernel: bf16, padded, pad columns zero
+            dl = dl_bf16
+        elif self.classes_pad == self.classes:
             dl = torch.empty((N, self.classes_pad), device=self.device, dtype=torch.bfloat16)
             ops.cast_bf16(dlogits.contiguous().float(), dl)
         else:
@@ -432,16 +443,63 @@ class Runtime(object):
         if x.device.type != 'cuda':
             raise B200Error('B200 runtime needs CUDA inputs (no CPU fallback); got %s' % x.device)
         training = self.model.training
-        if torch.is_grad_enabled():
-            return _NetFn.apply(x, self._anchor, self, training)
+        if torch.is_grad_enabled() and training:
+            out = _NetFn.apply(x, self._anchor, self, training)
+            out._b200_head = _HeadHandle(self, self._last_logits_pad)   # lets CrossEntropyLoss take the fused kernel
+            return out
+        # eval mode never tapes (BatchNorm backward with running statistics is not implemented): the logits carry no
+        # autograd history, so a backward() through them fails loudly instead of using batch-statistics formulas
         logits, _ = self.run_forward(x, training, False)
         return logits
 
     def run_forward(self, x, training, want_tape):
         raise NotImplementedError
 
-    def run_backward(self, tape, dlogits):
+    def run_backward(self, tape, dlogits, dl_bf16=None):
         raise NotImplementedError
+
+
+class _HeadHandle(object):
+    """Tag on the logits of a taped forward: the padded fp32 logits storage + the runtime that produced them."""
+    __slots__ = ('rt', 'logits_pad')
+
+    def __init__(self, rt, logits_pad):
+        self.rt, self.logits_pad = rt, logits_pad
+
+    def loss(self, logits, target, smooth_eps=0.0):
+        return _FusedCE.apply(logits, target, float(smooth_eps or 0.0), self)
+
+
+class _FusedCE(torch.autograd.Function):
+    """mean softmax cross-entropy with label smoothing (reference utils/cross_entropy.py:20-24,46-52) on the fused
+    kernel.  backward writes bf16 dlogits (already multiplied by the upstream gradient, read on the device) straight
+    into the buffer the classifier's dgrad/wgrad kernels consume; autograd only carries a zero-stride placeholder."""
+
+    @staticmethod
+    def forward(ctx, logits, target, eps, head):
+        pad, rt = head.logits_pad, head.rt
+        if logits.data_ptr() != pad.data_ptr() or logits.shape != (pad.shape[0], rt.classes) or \
+                target.shape != (pad.shape[0],) or target.dtype != torch.int64 or not target.is_cuda:
+            raise B200Error('fused cross-entropy: logits/target do not belong to this forward pass')
+        target = target.contiguous()
+        loss = torch.empty(1, device=pad.device, dtype=torch.float32)
+        rows = torch.empty(pad.shape[0], device=pad.device, dtype=torch.float32)
+        ops.softmax_ce(pad, target, rt.classes, eps, loss=loss, row_loss=rows)
+        ctx.head, ctx.eps = head, eps
+        ctx.save_for_backward(target)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        head, (target,) = ctx.head, ctx.saved_tensors
+        pad, rt = head.logits_pad, head.rt
+        up = gout.reshape(1)
+        if up.dtype != torch.float32 or not up.is_contiguous():
+            up = up.float().contiguous()
+        dl = torch.empty(pad.shape, device=pad.device, dtype=torch.bfloat16)
+        ops.softmax_ce(pad, target, rt.classes, ctx.eps, dlogits=dl, grad_scale_dev=up)
+        rt._fused_dl = dl
+        return rt._ce_dummy.expand(pad.shape[0], rt.classes), None, None, None
 
 
 class _NetFn(torch.autograd.Function):
@@ -451,6 +509,7 @@ class _NetFn(torch.autograd.Function):
     def forward(ctx, x, anchor, rt, training):
         logits, tape = rt.run_forward(x.detach(), training, True)
         ctx.rt, ctx.tape = rt, tape
+        rt._last_logits_pad = tape['head']['logits_pad']
         return logits
 
     @staticmethod
@@ -458,7 +517,15 @@ class _NetFn(torch.autograd.Function):
         rt, tape = ctx.rt, ctx.tape
         ctx.tape = None
         rt.arena.rebind_grads()
-        rt.run_backward(tape, dlogits)
+        rt.arena.grads_zero = False
+        side, rt._fused_dl = rt._fused_dl, None
+        if side is not None and (side.shape[0] != dlogits.shape[0] or side.device != dlogits.device):
+            side = None
+        if side is not None and not (dlogits.data_ptr() == rt._ce_dummy.data_ptr() and dlogits.stride() == (0, 0)):
+            # the logits had another consumer besides the fused loss: add its gradient (rare; torch glue)
+            dlogits = dlogits + side[:, :rt.classes].float()
+            side = None
+        rt.run_backward(tape, dlogits, dl_bf16=side)
         return None, None, None, None
 
 
@@ -519,22 +586,22 @@ class ResNetRuntime(Runtime):
                 # full 128B-swizzle TMA tile (4 loads per tile instead of 16 quarter-width ones).
                 xs = ops.input_prep(x, 16, s2d=True, border=True)      # [N, Hs+3, Ws+3, 16], data at (+2,+2)
                 desc = ops.make_desc(N, Hs + 3, Ws, 64, K, 4, 1, 1, 0, P=Hs, Q=Ws,
-                                     x_strides=(16, (Ws + 3) * 16, (Hs + 3) * (Ws + 3) * 16))
+                                     x_strides=(16, (Ws + 3) * 16, (Hs + 3) * (Ws + 3) * 16), algo_macs=K * 49 * Cin)
                 st['wgrad_desc'] = desc
                 if HALO_STEM and Ws + 3 <= 128:
                     # same bordered tensor described as the dense 4x4 / pad-0 convolution it is: the library runs it
                     # on the halo kernel (one 32-byte-row tile load per output row, weights stationary in smem)
-                    desc = ops.make_desc(N, Hs + 3, Ws + 3, 16, K, 4, 4, 1, 0, P=Hs, Q=Ws)
+                    desc = ops.make_desc(N, Hs + 3, Ws + 3, 16, K, 4, 4, 1, 0, P=Hs, Q=Ws, algo_macs=K * 49 * Cin)
                     if HALO_STEM_WGRAD:
                         st['wgrad_desc'] = desc
             else:
                 xs = ops.input_prep(x, 16, s2d=True)                   # [N, H/2, W/2, 16]
-                desc = ops.make_desc(N, Hs, Ws, 16, K, 4, 4, 1, 2, P=Hs, Q=Ws)
+                desc = ops.make_desc(N, Hs, Ws, 16, K, 4, 4, 1, 2, P=Hs, Q=Ws, algo_macs=K * 49 * Cin)
         else:
             xs = ops.input_prep(x, 16, s2d=False)
             ws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.bfloat16)
             ws[:, :, :Cin].copy_(self.stem_w32.view(K, 9, Cin))       # 432-element pad+cast of the 3-channel stem
-            desc = ops.make_desc(N, H, W, 16, K, 3, 3, 1, 1)
+            desc = ops.make_desc(N, H, W, 16, K, 3, 3, 1, 1, algo_macs=K * 9 * Cin)
         u = _Unit()
         u.conv, u.bn, u.act, u.x, u.desc = None, self.stem_bn, ACT_RELU, xs, desc
         self._conv_and_coeffs(u, xs, ws, training)
@@ -613,9 +680,9 @@ class ResNetRuntime(Runtime):
         tape = {'stem': stem, 'blocks': saved, 'head': head} if want_tape else None
         return out, tape
 
-    def run_backward(self, tape, dlogits):
+    def run_backward(self, tape, dlogits, dl_bf16=None):
         self._transpose_weights()
-        d = self._head_bwd(tape['head'], dlogits)
+        d = self._head_bwd(tape['head'], dlogits, dl_bf16)
         for spec, saved in zip(reversed(self.blocks), reversed(tape['blocks'])):
             d = self._block_bwd(spec, saved, d)
         self._stem_bwd(tape['stem'], d)
@@ -693,7 +760,7 @@ class MobileNetRuntime(Runtime):
         st, pad = self.stem_conv.stride[0], self.stem_conv.padding[0]
         u = _Unit()
         u.conv, u.bn, u.act, u.x = None, self.stem_bn, ACT_RELU6, xs
-        u.desc = ops.make_desc(N, H, W, 16, K, 3, 3, st, pad)
+        u.desc = ops.make_desc(N, H, W, 16, K, 3, 3, st, pad, algo_macs=K * 9 * Cin)
         u.z = ops.conv_fprop(xs, ws, u.desc)
         self._bn_coeffs(u, training)
         u.y = ops.bn_apply(u.z, u.scale, u.shift, ACT_RELU6)
@@ -728,9 +795,9 @@ class MobileNetRuntime(Runtime):
         tape = {'stem': stem, 'blocks': saved, 'head': head} if want_tape else None
         return out, tape
 
-    def run_backward(self, tape, dlogits):
+    def run_backward(self, tape, dlogits, dl_bf16=None):
         self._transpose_weights()
-        d = self._head_bwd(tape['head'], dlogits)
+        d = self._head_bwd(tape['head'], dlogits, dl_bf16)
         for spec, units in zip(reversed(self.blocks), reversed(tape['blocks'])):
             skip = d if spec['add_res'] else None   # out = bn(z) + x (no activation): the skip gradient is dy itself
             for j in range(len(units) - 1, -1, -1):

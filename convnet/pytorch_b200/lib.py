@@ -61,9 +61,9 @@ SIGNATURES = {
     "b200_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
     "b200_group_weight_expand": [_vp, _i, _i, _i, _i, _vp, _vp],
     "b200_group_wgrad_extract": [_vp, _i, _i, _i, _i, _vp, _vp],
-    "b200_softmax_ce": [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp],
+    "b200_softmax_ce": [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "b200_colsum_bf16": [_vp, _i, _i, _vp, _vp],
-    "b200_fused_sgd": [_vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _f, _f, _f, _vp, _i, _vp],
+    "b200_fused_sgd": [_vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _f, _f, _f, _vp, _i, _i, _vp],
     "b200_sumsq": [_vp, _ll, _vp, _vp, _vp],
     "b200_grad_coef": [_vp, _f, _i, _f, _f, _vp, _vp, _vp, _vp],
     "b200_last_error": [],

@@ -63,7 +63,13 @@ def stop_timing():
 
 
 def _conv_flops(d):
-    return 2 * d.N * d.P * d.Q * d.K * d.R * d.S * d.C
+    """ALGORITHMIC FLOPs of the convolution the reference runs (bench.py's roofline numerators): descriptors of
+    padded / re-laid problems (space-to-depth stem 7x7x3 -> 4x4x16, class count padded to 8, grouped convolutions
+    executed on a block-diagonal dense weight) carry the true MACs per output pixel in ``algo_macs``."""
+    macs = getattr(d, 'algo_macs', None)
+    if macs is None:
+        macs = d.K * d.R * d.S * d.C
+    return 2 * d.N * d.P * d.Q * macs
 
 
 def _chk(t, dtype, name):
@@ -82,11 +88,14 @@ def out_size(h, r, stride, pad_lo, pad_hi=None):
     return (h + pad_lo + pad_hi - r) // stride + 1
 
 
-def make_desc(N, H, W, C, K, R, S, stride, pad, P=None, Q=None, x_strides=(0, 0, 0)):
+def make_desc(N, H, W, C, K, R, S, stride, pad, P=None, Q=None, x_strides=(0, 0, 0), algo_macs=None):
     pad_h, pad_w = (pad, pad) if isinstance(pad, int) else pad
     P = out_size(H, R, stride, pad_h) if P is None else P
     Q = out_size(W, S, stride, pad_w) if Q is None else Q
-    return ConvDesc(N, H, W, C, K, R, S, stride, pad_h, pad_w, P, Q, *x_strides)
+    d = ConvDesc(N, H, W, C, K, R, S, stride, pad_h, pad_w, P, Q, *x_strides)
+    if algo_macs is not None:
+        d.algo_macs = int(algo_macs)      # python-side annotation only (not part of the C struct)
+    return d
 
 
 # ------------------------------------------------------------------------------------ convolution
@@ -368,12 +377,19 @@ def cast_bf16(src, dst):
 
 
 # ------------------------------------------------------------------------------------ loss / optimizer
-def softmax_ce(logits, target, classes, smooth_eps, grad_scale, loss, dlogits):
+def softmax_ce(logits, target, classes, smooth_eps, loss=None, row_loss=None, dlogits=None, grad_scale=1.0,
+               grad_scale_dev=None):
+    """logits fp32 [B, ld] (ld >= classes), target int64 [B].  loss (+ row_loss [B] scratch): mean loss, overwritten;
+    dlogits bf16 [B, ld] = grad_scale * (*grad_scale_dev) / B * dloss/dlogits (pad columns zeroed)."""
     B, ld = logits.shape
-    _chk(logits, torch.float32, "logits"); _chk(target, torch.int64, "target")
-    _l.check(_l.load().b200_softmax_ce(logits.data_ptr(), target.data_ptr(), B, int(classes), int(ld), float(smooth_eps or 0.0),
-                                       float(grad_scale), loss.data_ptr(), _l.ptr(dlogits), _stream()),
-             "b200_softmax_ce")
+    _chk(logits, torch.float32, "logits"); _chk(target, torch.int64, "target"); _chk(dlogits, bf16, "dlogits")
+    _chk(loss, torch.float32, "loss"); _chk(row_loss, torch.float32, "row_loss")
+    _chk(grad_scale_dev, torch.float32, "grad_scale_dev")
+    with _T('softmax_ce', 0, 4 * logits.numel()):
+        _l.check(_l.load().b200_softmax_ce(logits.data_ptr(), target.data_ptr(), B, int(classes), int(ld),
+                                           float(smooth_eps or 0.0), float(grad_scale), _l.ptr(grad_scale_dev),
+                                           _l.ptr(loss), _l.ptr(row_loss), _l.ptr(dlogits), _stream()),
+                 "b200_softmax_ce")
 
 
 def colsum_bf16(m, out):
@@ -382,12 +398,12 @@ def colsum_bf16(m, out):
 
 
 def fused_sgd(p32, g32, m32, p16, n, wd_count, lr, momentum, dampening, weight_decay, inv_scale, clip_coef,
-              first_step):
-    with _T('fused_sgd', 0, 22 * int(n)):
+              first_step, zero_grad=False):
+    with _T('fused_sgd', 0, (26 if zero_grad else 22) * int(n)):
         _l.check(_l.load().b200_fused_sgd(p32.data_ptr(), g32.data_ptr(), _l.ptr(m32), _l.ptr(p16), int(n),
                                           int(wd_count), float(lr), float(momentum), float(dampening),
                                           float(weight_decay), float(inv_scale), _l.ptr(clip_coef), int(bool(first_step)),
-                                          _stream()), "b200_fused_sgd")
+                                          int(bool(zero_grad)), _stream()), "b200_fused_sgd")
 
 
 def sumsq(g, n, out, workspace):

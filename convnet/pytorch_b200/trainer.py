@@ -105,9 +105,12 @@ class Trainer(object):
         self.graph_replays = 0                 # bench.py: launches replayed from graphs are not counted by the library
         self.graph_replayed_launches = 0
         self.world_size = dist.get_world_size() if (distributed and dist.is_initialized()) else 1
+        self._upstream_t, self._upstream_v = None, None
 
         if self.b200 is not None:
             self.model = model
+            if optimizer is not None and hasattr(optimizer, 'fold_zero_grad'):
+                optimizer.fold_zero_grad(True)     # the fused SGD pass also clears the gradient arena
             if distributed and self.world_size > 1:
                 self._broadcast_initial_state()
         elif distributed:
@@ -164,8 +167,8 @@ class Trainer(object):
         a new shape, unsupported configuration).  Gradients land in the arena exactly as in the eager path."""
         if not self._graph_eligible() or not inputs.is_cuda:
             return None
-        key = (tuple(inputs.shape), inputs.dtype, tuple(target.shape), target.dtype, self.loss_scale, self.grad_scale,
-               self._model.training)
+        # loss / gradient scales are NOT part of the key: they reach the kernels through a device scalar
+        key = (tuple(inputs.shape), inputs.dtype, tuple(target.shape), target.dtype, self._model.training)
         st = self._graphs.get(key)
         if st is None:
             st = self._graphs[key] = {'seen': 0, 'graph': None}
@@ -182,6 +185,7 @@ class Trainer(object):
                 return None
         st['x'].copy_(inputs, non_blocking=True)
         st['y'].copy_(target, non_blocking=True)
+        self._upstream()                          # refresh the device scalar if a scale changed
         st['graph'].replay()
         self.graph_replays += 1
         self.graph_replayed_launches += st['launches']
@@ -197,23 +201,40 @@ class Trainer(object):
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         n0 = lib.launch_count()
+        up = self._upstream()
         with torch.cuda.graph(graph, pool=self._graph_pool):
             out = self.model(x_s)
             loss = self.criterion(out, y_s)
-            bwd = loss
-            if self.grad_scale is not None:
-                bwd = bwd * self.grad_scale
-            if self.loss_scale is not None:
-                bwd = bwd * self.loss_scale
-            bwd.backward()
+            torch.autograd.backward(loss, grad_tensors=[up])
         st.update(graph=graph, x=x_s, y=y_s, out=out, loss=loss, launches=lib.launch_count() - n0)
+
+    def _upstream(self):
+        """d(scaled loss)/d(loss) = grad_scale * loss_scale (trainer.py:158-161 of the reference multiplies the loss)
+        as a persistent 0-dim device tensor handed to autograd.backward: no per-step scalar kernels, and a captured
+        graph reads the current value instead of a baked-in constant."""
+        v = 1.0
+        if self.grad_scale is not None:
+            v *= float(self.grad_scale)
+        if self.loss_scale is not None:
+            v *= float(self.loss_scale)
+        if self._upstream_t is None:
+            self._upstream_t = torch.empty((), device=self.b200.device, dtype=torch.float32)
+        if v != self._upstream_v:
+            self._upstream_t.fill_(v)
+            self._upstream_v = v
+        return self._upstream_t
 
     # ------------------------------------------------------------------ one optimisation step
     def _input_dtype(self):
         return torch.float if self.b200 is not None else self.dtype
 
     def _grad_norm(self, inputs_batch, target_batch, chunk_batch=1):
-        self.model.zero_grad()
+        if self.b200 is not None:
+            # nn.Module.zero_grad() only drops the views (p.grad = None): the kernels accumulate into the arena itself
+            self.b200.arena.zero_grad()
+            self.b200.arena.rebind_grads()
+        else:
+            self.model.zero_grad()
         for inputs, target in zip(inputs_batch.chunk(chunk_batch, dim=0), target_batch.chunk(chunk_batch, dim=0)):
             target = target.to(self.device)
             inputs = inputs.to(self.device, dtype=self._input_dtype())
@@ -258,11 +279,14 @@ class Trainer(object):
             if training:
                 if i == 0:
                     self.optimizer.pre_backward()
-                if self.grad_scale is not None:
-                    loss = loss * self.grad_scale
-                if self.loss_scale is not None:
-                    loss = loss * self.loss_scale
-                loss.backward()
+                if self.b200 is not None and loss.dim() == 0 and loss.dtype == torch.float32:
+                    torch.autograd.backward(loss, grad_tensors=[self._upstream()])
+                else:
+                    if self.grad_scale is not None:
+                        loss = loss * self.grad_scale
+                    if self.loss_scale is not None:
+                        loss = loss * self.loss_scale
+                    loss.backward()
 
         if training:
             if self.b200 is not None:

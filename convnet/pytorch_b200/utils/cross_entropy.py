@@ -1,8 +1,10 @@
 """Cross-entropy with label smoothing and soft targets; interface of utils/cross_entropy.py:14-85.
 
-On CUDA tensors produced by the B200 engine the loss is computed by the fused softmax-CE kernel
-(engine.B200CrossEntropy); this module is the host-side definition used on CPU (config C1) and as the
-semantic specification of that kernel.
+Logits produced by a taped forward of the B200 engine carry a ``_b200_head`` tag (engine._HeadHandle);
+``CrossEntropyLoss`` then runs the fused softmax-CE kernel (csrc/loss.cu, forward + backward, label smoothing
+included) through ``engine._FusedCE``.  Everything else -- CPU (config C1), soft targets, class weights,
+``reduction != 'mean'``, ``ignore_index >= 0`` -- uses the torch definition below, which is also the semantic
+specification of that kernel.
 """
 import torch
 import torch.nn as nn
@@ -65,12 +67,10 @@ class CrossEntropyLoss(nn.CrossEntropyLoss):
 
     def forward(self, input, target, smooth_dist=None):
         dist = self.smooth_dist if smooth_dist is None else smooth_dist
-        fused = getattr(input, '_b200_head', None)
-        if fused is not None and _is_long(target) and self.weight is None and dist is None \
-                and self.reduction == 'mean' and self.ignore_index < 0 or (
-                    fused is not None and _is_long(target) and self.weight is None and dist is None
-                    and self.reduction == 'mean' and self.ignore_index == -100):
-            return fused.loss(input, target, self.smooth_eps or 0.0)
+        head = getattr(input, '_b200_head', None)
+        if head is not None and _is_long(target) and target.is_cuda and self.weight is None and dist is None \
+                and self.reduction == 'mean' and self.ignore_index < 0 and self.from_logits:
+            return head.loss(input, target, self.smooth_eps or 0.0)
         return cross_entropy(input, target, weight=self.weight, ignore_index=self.ignore_index,
                              reduction=self.reduction, smooth_eps=self.smooth_eps, smooth_dist=dist,
                              from_logits=self.from_logits)

@@ -122,6 +122,9 @@ class B200SGD(torch.optim.Optimizer):
         self.inv_scale = 1.0
         self.extra_wd = (0.0, 0)      # (value, arena prefix length) from a folded WeightDecay regularizer
         self.coef_dev = None          # device scalar multiplied into the gradient (clip / GradSmooth)
+        # True: the kernel also clears the gradient arena (the zero_grad() of the next step, utils/optim.py:246-252
+        # of the reference, folded into this pass).  Trainer switches it on; stand-alone users keep p.grad after step()
+        self.fold_zero_grad = False
 
     def _bind_state(self):
         arena = self.rt.arena
@@ -142,7 +145,8 @@ class B200SGD(torch.optim.Optimizer):
             wd_val, wd_count = wd_val + g['weight_decay'], arena.total
         first = not self._have_momentum
         ops.fused_sgd(arena.p32, arena.g32, self.m32, arena.p16, arena.total, wd_count, g['lr'], g['momentum'],
-                      g['dampening'], wd_val, self.inv_scale, self.coef_dev, first)
+                      g['dampening'], wd_val, self.inv_scale, self.coef_dev, first, zero_grad=self.fold_zero_grad)
+        arena.grads_zero = bool(self.fold_zero_grad)
         arena.version += 1       # folded inference weights / transposed shadows derived from p16 are stale
         if g['momentum'] != 0 and first:
             self._have_momentum = True
@@ -189,6 +193,7 @@ class OptimRegime(Regime):
         self._clip = None
         self._device_state = {}
         self.last_grad_norm = None
+        self._fold_zero_grad = False
 
     # ------------------------------------------------------------------ construction helpers
     def _fresh_sgd(self):
@@ -316,9 +321,24 @@ class OptimRegime(Regime):
     def request_clip(self, max_norm):
         self._clip = float(max_norm)
 
+    def fold_zero_grad(self, enabled=True):
+        """B200: let the fused SGD kernel clear the gradient arena in its own pass (the next zero_grad() is then free).
+        p.grad reads zero after step(); Trainer enables it, nothing else does."""
+        self._fold_zero_grad = bool(enabled)
+
     def step(self, *args, **kwargs):
         if self._b200 is not None and isinstance(self.optimizer, B200SGD):
+            self.optimizer.fold_zero_grad = self._fold_zero_grad
             return self._step_b200()
+        if self._b200 is not None:
+            # any other torch optimizer on the arena views: the unscale (loss scale x world size) and the clip that
+            # Trainer delegates to this class (set_grad_unscale / request_clip) are applied here, as in the
+            # non-foldable branch of _step_b200 (reference: trainer.py:165-172)
+            if self._inv_scale != 1.0:
+                self._b200.arena.g32.mul_(self._inv_scale)
+            if self._clip is not None and self._clip > 0:
+                self.last_grad_norm = torch.nn.utils.clip_grad_norm_(self.parameters, self._clip)
+            self._clip = None
         if self.use_float_copy:
             copy_params_grad(self.parameters, self._original_parameters)
         self.regularizer.pre_step()

@@ -161,10 +161,13 @@ int b200_group_wgrad_extract(const float* dw_dense, int K, int T, int C, int gro
 /* ---- loss (csrc/loss.cu) ----------------------------------------------------------------------
  * replaces utils/cross_entropy.py:14-67 (F.cross_entropy / label smoothing) forward+backward.
  * logits/dlogits rows have pitch ld >= classes (columns [classes, ld) are padding: ignored on read,
- * zeroed in dlogits).  *loss (fp32, zeroed by caller) accumulates mean_i loss_i;
- * dlogits (bf16) = grad_scale/B * dloss_i/dlogits. */
+ * zeroed in dlogits).  loss != NULL: row_loss[B] (scratch) receives the per-sample losses and *loss (fp32, device,
+ * overwritten) their mean, summed in a fixed order.  dlogits != NULL: dlogits (bf16) = grad_scale *
+ * (*grad_scale_dev if non-NULL) / B * dloss_i/dlogits -- the device scalar is the upstream gradient of the loss
+ * (loss scaling, trainer.py:158-161) so that no host value is baked into a captured graph. */
 int b200_softmax_ce(const float* logits, const long long* target, int B, int classes, int ld, float smooth_eps,
-                    float grad_scale, float* loss, void* dlogits_bf16, b200_stream_t stream);
+                    float grad_scale, const float* grad_scale_dev, float* loss, float* row_loss, void* dlogits_bf16,
+                    b200_stream_t stream);
 /* column sums of a bf16 [B][K] matrix accumulated into fp32 out[K] (fc bias gradient) */
 int b200_colsum_bf16(const void* m, int B, int K, float* out, b200_stream_t stream);
 
@@ -173,10 +176,11 @@ int b200_colsum_bf16(const void* m, int B, int K, float* out, b200_stream_t stre
  * (utils/regularization.py:127-131), torch.optim.SGD.step (utils/optim.py:254-264) and the
  * fp32->low-precision copy-back (utils/optim.py:43-47,263-264) in ONE pass over flat arenas.
  * Elements [0, wd_count) receive weight decay. hyper: device or host pointer is NOT used; values
- * are passed by value except clip_coef_dev (device scalar multiplied into g, may be NULL). */
-int b200_fused_sgd(float* p32, const float* g32, float* m32, void* p16, long long n, long long wd_count,
+ * are passed by value except clip_coef_dev (device scalar multiplied into g, may be NULL).
+ * zero_grad != 0: g32 is cleared in the same pass (OptimRegime.zero_grad of the NEXT step, utils/optim.py:246-252). */
+int b200_fused_sgd(float* p32, float* g32, float* m32, void* p16, long long n, long long wd_count,
                    float lr, float momentum, float dampening, float weight_decay, float inv_scale,
-                   const float* clip_coef_dev, int first_step, b200_stream_t stream);
+                   const float* clip_coef_dev, int first_step, int zero_grad, b200_stream_t stream);
 /* sum of squares of a flat fp32 array -> *out (device, fp32); out is overwritten */
 int b200_sumsq(const float* g, long long n, float* out, float* workspace, b200_stream_t stream);
 /* GradSmooth (utils/regularization.py:198-224) / clip_grad_norm_ (trainer.py:171-172) on device:

@@ -39,10 +39,47 @@ def synth(batch, shape, classes, seed=0):
     return torch.randn(batch, *shape, generator=g), torch.randint(0, classes, (batch,), generator=g)
 
 
+def mobilenet_v2_fixture(ref_models, ref_trainer, ref_optim, ref_ce):
+    """MobileNet-v2 (config C4's family) through the reference Trainer on 16 x 3x96x96 inputs, default init (seed 123),
+    classifier dropout ACTIVE (generator re-seeded before every step so that a restatement draws the same masks):
+    step 1 is recorded in full (logits, loss, gradient norms + heads, post-step parameter statistics), step 2 by its
+    loss.  Default-init MobileNet-v2 is ill-conditioned (fp32 vs fp64 gradients of the SAME code differ by 3e-3..1e-2,
+    measured with the restatement), so only step 1 supports tight bounds.  The model itself is re-created from the
+    seed (test_model_factories_match_reference_init pins that)."""
+    torch.manual_seed(123)
+    model = ref_models.mobilenet_v2(dataset='imagenet')
+    x, y = synth(16, (3, 96, 96), 1000)
+    opt = ref_optim.OptimRegime(model, model.regime)
+    tr = ref_trainer.Trainer(model, ref_ce.CrossEntropyLoss(), opt, device_ids=None, device='cpu',
+                             dtype=torch.float, print_freq=1000)
+    model.train()
+    opt.zero_grad(); opt.update(0, 0)
+    wd_names = [n for n, _ in opt.regularizer.regularization_list[0]._named_parameters]
+    torch.manual_seed(1000)
+    out = model(x); loss = tr.criterion(out, y); loss.backward()
+    gn = {n: float(p.grad.norm()) for n, p in model.named_parameters()}
+    gh = {n: p.grad.flatten()[:4].clone().numpy() for n, p in model.named_parameters()}
+    opt.step()
+    tr.training_steps += 1
+    post = tensor_stats(model.state_dict())
+    torch.manual_seed(1001)
+    _, loss2, _ = tr._step(x, y, training=True)
+    np.savez(os.path.join(OUT, 'mobilenet_v2_summary.npz'), x=x.numpy(), y=y.numpy(), logits=out.detach().numpy(),
+             loss=np.float64(float(loss)), loss_step2=np.float64(float(loss2)), grad_names=np.array(list(gn.keys())),
+             grad_norms=np.array(list(gn.values())), grad_heads=np.stack([gh[n] for n in gn]),
+             wd_names=np.array(wd_names), post_names=np.array(list(post.keys())),
+             post_sums=np.array([post[k]['sum'] for k in post]), post_abs=np.array([post[k]['abs'] for k in post]))
+    print('mobilenet_v2 fixture written')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref_models, ref_trainer, ref_optim, ref_ce = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'mobilenet_v2':   # regenerate only this fixture
+        mobilenet_v2_fixture(ref_models, ref_trainer, ref_optim, ref_ce)
+        return
+    mobilenet_v2_fixture(ref_models, ref_trainer, ref_optim, ref_ce)
 
     # ---- 1. initialisation of the four model families under the CLI seed (main.py:114-115,137) ----
     init = {}

@@ -15,6 +15,10 @@ Follows, line by line:
   CrossEntropyLoss                 utils/cross_entropy.py:14-67
   Trainer._step + OptimRegime.step trainer.py:106-177, utils/optim.py:254-264, utils/regularization.py:127-131,
                                    torch.optim.SGD (momentum, first step m = g)   -> ``sgd_step``
+  MobileNet_v2.forward             models/mobilenet_v2.py:151-156  -> ``forward_mobilenet_v2``
+  ExpandedConv2d.forward           models/mobilenet_v2.py:39-73    (1x1 expand/BN/ReLU6, depthwise 3x3/BN/ReLU6,
+                                   1x1 project/BN, identity skip when stride == 1 and C_in == C_out)
+  MobileNet WeightDecay filter     models/mobilenet_v2.py:25-36    -> ``is_decayed`` (state-dict aware)
 ``quant`` emulates the storage precision of the CUDA path: a straight-through bf16 round placed where the
 kernels store bf16 (conv outputs, BN/activation outputs, pooled features, their incoming gradients) --
 the "T2" oracle of SURVEY.md section 8c.
@@ -88,8 +92,91 @@ def _basic(x, sd, p, stride, training, bufs, quant):
     return _q(F.relu(out + _skip(x, sd, p, stride, training, bufs, quant)), quant)
 
 
-def forward(sd, x, training=True, buffers_out=None, quant=False):
-    """logits of a reference-layout ResNet ``state_dict`` (cifar or imagenet variant, basic or bottleneck)."""
+# strides of the 17 ExpandedConv2d stages (models/mobilenet_v2.py:91-109: layers_config)
+_MBV2_STRIDES = (1, 2, 1, 2, 1, 1, 2, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1)
+
+
+def _mb_conv_bn(x, sd, conv, bn, stride, pad, act, training, bufs, quant, skip=None, trace=None):
+    """conv -> BN -> [ReLU6] (+ identity skip for the linear bottleneck output), with the storage roundings of the
+    kernel pipeline: after the conv and after the BN/activation(/add) pass."""
+    z = _conv(x, sd, conv, stride, pad, quant)          # groups inferred from the weight shape (depthwise: C/1)
+    y = _bn(z, sd, bn, training, bufs, quant)
+    if act:
+        y = F.relu6(y)
+    if skip is not None:
+        y = y + skip
+    y = _q(y, quant)
+    if trace is not None:
+        trace.append({'conv': conv, 'bn': bn, 'stride': stride, 'pad': pad, 'act': act, 'x': x, 'skip': skip, 'y': y})
+    return y
+
+
+def mobilenet_v2_unit_trace(sd, x, y, quant=True):
+    """Teacher-forcing data for unit-level parity: every conv+BN(+ReLU6)(+skip) unit of one training forward/backward
+    with its input ``x``, skip input, output ``y`` and the gradient ``dy`` arriving at its output (all detached).
+    Default-init MobileNet-v2 is chaotic end to end (see make_golden.mobilenet_v2_fixture); unit by unit, on the real
+    activations and gradients, the comparison is well posed."""
+    work = {k: (v.detach().clone().requires_grad_(True) if k in param_names(sd) else v) for k, v in sd.items()}
+    trace = []
+    logits = forward_mobilenet_v2(work, x, True, {}, quant, 0.0, trace=trace)
+    loss = cross_entropy(logits, y)
+    dys = torch.autograd.grad(loss, [u['y'] for u in trace])
+    units = []
+    for u, dy in zip(trace, dys):
+        units.append({k: (v.detach() if torch.is_tensor(v) else v) for k, v in u.items()})
+        units[-1]['dy'] = dy.detach()
+    return logits.detach(), loss.detach(), units
+
+
+def mobilenet_v2_unit_vjp(sd, unit, quant=True, dtype=torch.float64):
+    """Local reference of one traced unit in ``dtype``: output y and the vector-Jacobian products of ``dy`` with
+    respect to the unit input, the conv weight and the BN affine parameters (same storage roundings as the net)."""
+    x = unit['x'].to(dtype).requires_grad_(True)
+    names = [unit['conv'] + '.weight', unit['bn'] + '.weight', unit['bn'] + '.bias']
+    local = {k: v for k, v in sd.items() if k.startswith(unit['conv'] + '.') or k.startswith(unit['bn'] + '.')}
+    local = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in local.items()}
+    for n in names:
+        local[n] = local[n].detach().clone().requires_grad_(True)
+    skip = unit['skip'].to(dtype) if unit['skip'] is not None else None
+    yy = _mb_conv_bn(x, local, unit['conv'], unit['bn'], unit['stride'], unit['pad'], unit['act'], True, None, quant,
+                     skip=skip)
+    grads = torch.autograd.grad(yy, [x] + [local[n] for n in names], unit['dy'].to(dtype))
+    return yy.detach(), grads[0], grads[1], grads[2], grads[3]
+
+
+def forward_mobilenet_v2(sd, x, training=True, buffers_out=None, quant=False, dropout_p=0.0, trace=None):
+    """logits of a reference-layout MobileNet-v2 ``state_dict`` (models/mobilenet_v2.py:85-156)."""
+    x = _q(x, quant)
+    x = _mb_conv_bn(x, sd, 'features.conv0.0', 'features.conv0.1', 2, 1, True, training, buffers_out, quant, trace=trace)
+    i = 0
+    while 'features.bottleneck%d.block.0.weight' % i in sd:
+        p = 'features.bottleneck%d.block' % i
+        stride = _MBV2_STRIDES[i]
+        inp = x
+        j = 0
+        if sd[p + '.0.weight'].shape[1] != 1:        # expansion != 1: the block starts with the 1x1 expand conv
+            x = _mb_conv_bn(x, sd, p + '.0', p + '.1', 1, 0, True, training, buffers_out, quant, trace=trace)
+            j = 3
+        x = _mb_conv_bn(x, sd, '%s.%d' % (p, j), '%s.%d' % (p, j + 1), stride, 1, True, training, buffers_out, quant,
+                        trace=trace)
+        w_out = sd['%s.%d.weight' % (p, j + 3)]
+        add_res = stride == 1 and inp.size(1) == w_out.shape[0]
+        x = _mb_conv_bn(x, sd, '%s.%d' % (p, j + 3), '%s.%d' % (p, j + 4), 1, 0, False, training, buffers_out, quant,
+                        skip=inp if add_res else None, trace=trace)
+        i += 1
+    x = _mb_conv_bn(x, sd, 'features.conv1.0', 'features.conv1.1', 1, 0, True, training, buffers_out, quant,
+                    trace=trace)
+    x = _q(x.mean((2, 3)), quant)
+    if training and dropout_p > 0:
+        x = F.dropout(x, dropout_p, True)              # same torch generator stream as nn.Dropout in the reference
+    return F.linear(x, sd['classifier.1.weight'], sd['classifier.1.bias'])
+
+
+def forward(sd, x, training=True, buffers_out=None, quant=False, dropout_p=0.0):
+    """logits of a reference-layout ``state_dict``: ResNet (cifar or imagenet variant, basic or bottleneck; also
+    ResNeXt, whose grouped convolutions are inferred from the weight shapes) or MobileNet-v2."""
+    if 'features.conv0.0.weight' in sd:
+        return forward_mobilenet_v2(sd, x, training, buffers_out, quant, dropout_p)
     x = _q(x, quant)
     imagenet = sd['conv1.weight'].shape[-1] == 7
     if imagenet:
@@ -118,10 +205,15 @@ def cross_entropy(logits, target, smooth_eps=0.0):
     return (-((1.0 - u - smooth_eps) * picked + u * lsm.sum(-1))).mean()
 
 
-def is_decayed(name):
-    """membership of the reference's WeightDecay filter (models/resnet.py:34-40): not a bias, not in a BN."""
+def is_decayed(name, sd=None):
+    """membership of the reference's WeightDecay filter: ResNet family (models/resnet.py:34-40) -- not a bias, not in
+    a BN; MobileNet-v2 (models/mobilenet_v2.py:25-36, needs ``sd``) -- weights of nn.Linear and of the NON-depthwise
+    convolutions only."""
     if name.endswith('bias'):
         return False
+    if name.startswith('features.') or name.startswith('classifier.'):
+        w = sd[name]
+        return w.dim() == 2 or (w.dim() == 4 and w.shape[1] != 1)
     return not re.search(r'(^|\.)bn\d*\.|downsample\.1\.', name)
 
 
@@ -130,12 +222,12 @@ def param_names(sd):
                                   or k.endswith('num_batches_tracked'))]
 
 
-def loss_and_grads(sd, x, y, smooth_eps=0.0, quant=False, training=True):
+def loss_and_grads(sd, x, y, smooth_eps=0.0, quant=False, training=True, dropout_p=0.0):
     """One forward/backward: returns logits, loss, {param: grad}, updated BN buffers."""
     names = param_names(sd)
     work = {k: (v.detach().clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
     bufs = {}
-    logits = forward(work, x, training=training, buffers_out=bufs, quant=quant)
+    logits = forward(work, x, training=training, buffers_out=bufs, quant=quant, dropout_p=dropout_p)
     loss = cross_entropy(logits, y, smooth_eps)
     grads = torch.autograd.grad(loss, [work[k] for k in names])
     return logits.detach(), loss.detach(), dict(zip(names, grads)), bufs
@@ -146,7 +238,7 @@ def sgd_step(sd, grads, momentum_buf, lr, momentum=0.9, weight_decay=1e-4, loss_
     new_sd, new_m = dict(sd), {}
     for k, g in grads.items():
         g = g / loss_scale
-        if is_decayed(k):
+        if is_decayed(k, sd):
             g = g + weight_decay * sd[k]
         m = g.clone() if momentum_buf.get(k) is None else momentum * momentum_buf[k] + g
         new_m[k] = m

@@ -60,10 +60,12 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _check_step(ref, mine, x, y, cos_min=0.9, gcos=0.99, grel=0.15):
-    """T1: bf16 pipeline vs fp32 torch.  The thresholds are loose on purpose: at the tiny batches used here the
-    inherent bf16-storage drift is large (the bf16-emulating oracle itself sits at cos ~0.996 vs fp32); the tight
-    comparison is the T2 test against that oracle."""
+def _check_step(ref, mine, x, y, logit_tol=1e-2, loss_tol=3e-2, cos_min=0.95, gcos=0.998, grel=8e-2):
+    """T1 of SURVEY.md section 8c (semantic tier): the bf16 pipeline vs the same model in fp32 under stock torch on
+    identical bf16-rounded parameters and inputs.  Bounds are the survey's own: logits rel-L2 <= 1e-2, |d loss| <= 3e-2,
+    global gradient cos >= 0.998 and rel-L2 <= 8e-2, every gradient tensor cos >= 0.95 (inherent bf16-storage drift of
+    an ideal pipeline x ~1.5-2; see the calibration table there).  Batches are >= 32 samples."""
+    assert x.shape[0] >= 32, 'parity tests run at >= 32 samples (tiny batches create near-dead BN channels)'
     ref.train(); mine.train()
     xq = x.to(torch.bfloat16).float()
     ref.zero_grad()
@@ -76,26 +78,23 @@ def _check_step(ref, mine, x, y, cos_min=0.9, gcos=0.99, grel=0.15):
     loss_m.backward()
     torch.cuda.synchronize()
     assert lo_m.shape == lo_r.shape
-    assert _rel(lo_m, lo_r) < 1e-2, 'logits rel-L2 %.3e' % _rel(lo_m, lo_r)
-    assert abs(float(loss_m) - float(loss_r)) < 3e-2
     gm = torch.cat([p.grad.flatten() for p in mine.parameters()])
     gr = torch.cat([p.grad.flatten() for p in ref.parameters()])
-    print('T1 logits rel %.3e  grad cos %.5f rel %.3e' % (_rel(lo_m, lo_r), _cos(gm, gr), _rel(gm, gr)))
+    per = sorted((_cos(p.grad, q.grad), n) for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters())
+                 if float(q.grad.norm()) > 0)
+    print('T1 logits rel %.3e  dloss %.3e  grad cos %.5f rel %.3e  worst tensors %s'
+          % (_rel(lo_m, lo_r), abs(float(loss_m) - float(loss_r)), _cos(gm, gr), _rel(gm, gr), per[:3]))
+    assert _rel(lo_m, lo_r) < logit_tol, 'logits rel-L2 %.3e' % _rel(lo_m, lo_r)
+    assert abs(float(loss_m) - float(loss_r)) < loss_tol
     assert _cos(gm, gr) > gcos, 'global grad cos %.5f' % _cos(gm, gr)
     assert _rel(gm, gr) < grel, 'global grad rel %.3e' % _rel(gm, gr)
-    worst = 1.0
-    for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
-        if float(q.grad.norm()) == 0:
-            continue
-        c = _cos(p.grad, q.grad)
-        worst = min(worst, c)
-        assert c > cos_min, 'grad cos of %s = %.4f' % (n, c)
+    assert per[0][0] > cos_min, 'grad cos of %s = %.4f' % (per[0][1], per[0][0])
     for (n, b), (_, c) in zip(mine.named_buffers(), ref.named_buffers()):
         if 'num_batches' in n:
             assert int(b) == int(c)
         else:
             assert _rel(b, c) < 2e-2, 'buffer %s rel %.3e' % (n, _rel(b, c))
-    return worst
+    return per[0][0]
 
 
 def test_resnet20_cifar_step():
@@ -106,16 +105,16 @@ def test_resnet20_cifar_step():
 
 def test_resnet18_imagenet_step():
     from convnet.pytorch_b200.models import resnet
-    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=18), (3, 128, 128), 1000, batch=16)
+    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=18), (3, 128, 128), 1000, batch=32)
     _check_step(ref, mine, x, y)
 
 
-def _check_against_bf16_oracle(mine, ref, x, y, logit_tol=2e-3, grad_tol=5e-2, cos_min=0.98):
-    """T2 of SURVEY.md section 8c: the CPU oracle with bf16 rounding at exactly the points where the kernels
-    store bf16 -- remaining differences are accumulation order only.  Typical values are logits 1e-6..1e-4 and
-    global gradient rel-L2 ~6e-3; the bounds leave room for test-net states with near-dead BN channels
-    (tiny variance -> 1/sqrt(eps) gain on a flipped bf16 rounding), which the 8-sample batches here can produce."""
+def _check_against_bf16_oracle(mine, ref, x, y, logit_tol=1e-3, grad_tol=1e-2, cos_min=0.999):
+    """T2 of SURVEY.md section 8c (bit-level intent): the CPU oracle with bf16 rounding at exactly the points where the
+    kernels store bf16 -- remaining differences are accumulation order only.  Bounds are the survey's own: logits
+    rel-L2 <= 1e-3, global gradient rel-L2 <= 1e-2, every gradient tensor cos >= 0.999; batches are >= 32 samples."""
     from oracle import ref_model
+    assert x.shape[0] >= 32
     sd = {k: v.detach().cpu().clone() for k, v in ref.state_dict().items()}
     mine.train()
     mine._b200.arena.zero_grad()
@@ -124,18 +123,15 @@ def _check_against_bf16_oracle(mine, ref, x, y, logit_tol=2e-3, grad_tol=5e-2, c
     loss.backward()
     torch.cuda.synchronize()
     o_logits, o_loss, o_grads, o_bufs = ref_model.loss_and_grads(sd, x.cpu(), y.cpu(), quant=True)
-    assert _rel(lo.cpu(), o_logits) < logit_tol, 'logits vs bf16 oracle %.3e' % _rel(lo.cpu(), o_logits)
-    assert abs(float(loss) - float(o_loss)) < 5e-3
     gm = torch.cat([p.grad.cpu().flatten() for _, p in mine.named_parameters()])
     go = torch.cat([o_grads[n].flatten() for n, _ in mine.named_parameters()])
-    worst = sorted(((_rel(p.grad.cpu(), o_grads[n]), n) for n, p in mine.named_parameters()
-                    if float(o_grads[n].norm()) > 0), reverse=True)[:5]
-    print('T2 logits rel %.3e grad rel %.3e worst %s' % (_rel(lo.cpu(), o_logits), _rel(gm, go), worst))
+    per = sorted((_cos(p.grad.cpu(), o_grads[n]), n) for n, p in mine.named_parameters() if float(o_grads[n].norm()) > 0)
+    print('T2 logits rel %.3e  dloss %.3e  grad rel %.3e  worst tensors %s'
+          % (_rel(lo.cpu(), o_logits), abs(float(loss) - float(o_loss)), _rel(gm, go), per[:3]))
+    assert _rel(lo.cpu(), o_logits) < logit_tol, 'logits vs bf16 oracle %.3e' % _rel(lo.cpu(), o_logits)
+    assert abs(float(loss) - float(o_loss)) < 5e-3
     assert _rel(gm, go) < grad_tol, 'global grad rel vs bf16 oracle %.3e' % _rel(gm, go)
-    for n, p in mine.named_parameters():
-        if float(o_grads[n].norm()) > 0:
-            c = _cos(p.grad.cpu(), o_grads[n])
-            assert c > cos_min, 'grad cos of %s vs bf16 oracle = %.5f' % (n, c)
+    assert per[0][0] > cos_min, 'grad cos of %s vs bf16 oracle = %.5f' % (per[0][1], per[0][0])
     for n, b in mine.named_buffers():
         if 'running' in n:
             assert _rel(b.cpu(), o_bufs[n]) < 1e-3, n
@@ -149,19 +145,19 @@ def test_resnet20_against_bf16_oracle():
 
 def test_resnet18_imagenet_against_bf16_oracle():
     from convnet.pytorch_b200.models import resnet
-    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=18), (3, 64, 64), 1000, batch=8)
+    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=18), (3, 64, 64), 1000, batch=32)
     _check_against_bf16_oracle(mine, ref, x, y)
 
 
 def test_resnet50_imagenet_against_bf16_oracle():
     from convnet.pytorch_b200.models import resnet
-    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=50), (3, 64, 64), 1000, batch=8)
+    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=50), (3, 64, 64), 1000, batch=32)
     _check_against_bf16_oracle(mine, ref, x, y)
 
 
 def test_resnet50_imagenet_step_and_eval():
     from convnet.pytorch_b200.models import resnet
-    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=50), (3, 224, 224), 1000, batch=8)
+    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=50), (3, 224, 224), 1000, batch=32)
     _check_step(ref, mine, x, y)
     ref.eval(); mine.eval()
     with torch.no_grad():
@@ -208,73 +204,129 @@ def test_state_dict_roundtrip_with_reference_layout():
         assert v.shape == sd[k].shape and torch.equal(v.cpu().float(), sd[k].float()), k
 
 
-def _emulate_bf16_storage(model):
-    """straight-through bf16 rounding after every conv / BN / activation / pooling output of a torch model:
-    the storage precision of the kernel pipeline (cf. oracle.ref_model, which does the same for ResNets)."""
-    import torch.nn as nn
-    from oracle.ref_model import _STRound
-    kinds = (nn.Conv2d, nn.BatchNorm2d, nn.ReLU, nn.ReLU6, nn.AdaptiveAvgPool2d, nn.MaxPool2d)
-    for m in model.modules():
-        if isinstance(m, kinds):
-            if isinstance(m, (nn.ReLU, nn.ReLU6)):
-                m.inplace = False
-            m.register_forward_hook(lambda mod, inp, out: _STRound.apply(out))
-    return model
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
 
 
-def test_mobilenet_v2_step():
-    """MobileNet-v2 (depthwise path) vs stock torch: fp32 (T1, loose) and with bf16 storage emulated by hooks (T2).
-    Dropout is disabled so that both sides see the same network."""
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2).cpu()
+
+
+def test_mobilenet_v2_against_reference_pinned_oracle():
+    """MobileNet-v2 (config C4, depthwise path) against oracle.ref_model.forward_mobilenet_v2, which
+    tests/test_oracle_golden.py pins to the unmodified reference.  Dropout is disabled so both sides see one network.
+
+    Default-init MobileNet-v2 is chaotic under ANY reduced precision: the same fp32 code differs from fp64 by 3e-3..1e-2
+    in its gradients and an ideal bf16-storage pipeline reaches only cos ~0.5 against fp32 (oracle/make_golden.py).
+    A whole-network gradient bound would therefore say nothing, so the check has three parts:
+      1. whole-network FORWARD vs the bf16-storage oracle: logits, loss, running statistics;
+      2. TEACHER-FORCED unit parity: each of the 52 conv+BN(+ReLU6)(+skip) units is run through the kernels on the
+         oracle's own input / skip / output-gradient tensors and compared with a local fp64 reference of that unit
+         (output, input gradient, weight gradient, d gamma, d beta) -- well posed, no error compounding;
+      3. whole-network gradient drift from stock torch fp32 no larger than twice the ideal bf16 pipeline's own drift."""
     from convnet.pytorch_b200.models import mobilenet_v2
+    from convnet.pytorch_b200 import ops
+    from oracle import ref_model
 
     def factory(**cfg):
         m = mobilenet_v2(**cfg)
         m.classifier[0].p = 0.0
         return m
-    # default init (no zero-initialised BN in this family) at 128x128 / batch 32: with fewer samples the network is
-    # chaotic under bf16 storage (the torch emulation itself then drops to per-tensor cos ~0.6 against fp32)
     ref, mine, x, y = _pair(factory, dict(dataset='imagenet'), (3, 128, 128), 1000, steps=0, batch=32)
-    xq = x.to(torch.bfloat16).float()
-    mine.train(); mine._b200.arena.zero_grad()
+    rt = mine._b200
+    sd = {k: v.detach().cpu().clone() for k, v in ref.state_dict().items()}
+    o_logits, o_loss, units = ref_model.mobilenet_v2_unit_trace(sd, x.cpu(), y.cpu())
+
+    # ---- 1. whole-network forward (+ 3: gradients) -----------------------------------------------------------
+    mine.train(); rt.arena.zero_grad()
     lo_m = mine(x)
-    F.cross_entropy(lo_m, y).backward()
+    loss_m = F.cross_entropy(lo_m, y)
+    loss_m.backward()
     torch.cuda.synchronize()
     gm = torch.cat([p.grad.flatten() for p in mine.parameters()]).clone()
-    emu = _emulate_bf16_storage(copy.deepcopy(ref)).train()
-    emu.zero_grad()
-    lo_e = emu(xq)
-    F.cross_entropy(lo_e, y).backward()
-    ge = torch.cat([p.grad.flatten() for p in emu.parameters()])
+    print('MBv2 forward vs oracle: logits rel %.3e  dloss %.3e' % (_rel(lo_m.cpu(), o_logits),
+                                                                  abs(float(loss_m) - float(o_loss))))
+    assert _rel(lo_m.cpu(), o_logits) < 2e-2 and abs(float(loss_m) - float(o_loss)) < 2e-2
+    _, _, o_grads, o_bufs = ref_model.loss_and_grads(sd, x.cpu(), y.cpu(), quant=True)
+    for n, b in mine.named_buffers():
+        if 'running' in n:
+            assert _rel(b.cpu(), o_bufs[n]) < 5e-3, n
     ref.train(); ref.zero_grad()
-    lo_r = ref(xq)
-    F.cross_entropy(lo_r, y).backward()
-    gr = torch.cat([p.grad.flatten() for p in ref.parameters()])
-    print('MBv2 vs fp32: logits %.3e grad cos %.5f | emulation vs fp32: logits %.3e grad cos %.5f | vs emulation: '
-          'logits %.3e grad cos %.5f rel %.3e' % (_rel(lo_m, lo_r), _cos(gm, gr), _rel(lo_e, lo_r), _cos(ge, gr),
-                                                  _rel(lo_m, lo_e), _cos(gm, ge), _rel(gm, ge)))
-    # our drift from fp32 must be of the size of the ideal bf16-storage pipeline's own drift
-    assert _rel(lo_m, lo_r) < 2.0 * _rel(lo_e, lo_r) + 1e-3
-    assert _cos(gm, gr) > 1.0 - 2.0 * (1.0 - _cos(ge, gr)) - 1e-3
-    assert _rel(lo_m, lo_e) < 2.0 * _rel(lo_e, lo_r) + 1e-3 and _cos(gm, ge) > 1.0 - 2.5 * (1.0 - _cos(ge, gr)) - 1e-3
+    F.cross_entropy(ref(x.to(torch.bfloat16).float()), y).backward()
+    gr = torch.cat([p.grad.flatten() for p in ref.parameters()]).cpu()
+    go = torch.cat([o_grads[n].flatten() for n, _ in mine.named_parameters()])
+    print('MBv2 grad cos: mine/fp32 %.4f  oracle-bf16/fp32 %.4f  mine/oracle-bf16 %.4f'
+          % (_cos(gm.cpu(), gr), _cos(go, gr), _cos(gm.cpu(), go)))
+    assert _cos(gm.cpu(), gr) > 1.0 - 2.0 * (1.0 - _cos(go, gr)) - 1e-3
+
+    # ---- 2. teacher-forced units ------------------------------------------------------------------------------
+    flat = [(None, None, rt.stem_bn, None, 'features.conv0.0')]
+    for spec in rt.blocks:
+        for kind, conv, bn, act in spec['units']:
+            flat.append((kind, conv, bn, act, conv.slot.name[:-len('.weight')]))
+    assert len(flat) == len(units) and all(f[4] == u['conv'] for f, u in zip(flat, units))
+    params = dict(mine.named_parameters())
+    rt._transpose_weights()
+    worst = {}
+    for (kind, conv, bn, act, cname), u in zip(flat, units):
+        y_ref, dx_ref, dw_ref, dg_ref, db_ref = ref_model.mobilenet_v2_unit_vjp(sd, u)
+        rt.arena.zero_grad()
+        dy = _nhwc(u['dy'])
+        if kind is None:                                   # stem: NCHW fp32 network input, no input gradient
+            out, st = rt._stem_fwd(u['x'].cuda(), True)
+            rt._stem_bwd(st, dy)
+            dx = None
+        else:
+            skip = _nhwc(u['skip']) if u['skip'] is not None else None
+            uu = rt._mb_unit_fwd(_nhwc(u['x']), kind, conv, bn, act, True, residual=skip)
+            out = uu.y
+            dz, _ = rt._bn_bwd(uu, dy, None, act)
+            dx = rt._mb_conv_bwd(kind, uu, dz)
+        rt._wgrad_join()
+        torch.cuda.synchronize()
+        got = {'y': _rel(_nchw(out), y_ref), 'dw': _rel(params[cname + '.weight'].grad.cpu(), dw_ref),
+               'dgamma': _rel(params[u['bn'] + '.weight'].grad.cpu(), dg_ref),
+               'dbeta': _rel(params[u['bn'] + '.bias'].grad.cpu(), db_ref)}
+        if dx is not None:
+            got['dx'] = _rel(_nchw(dx), dx_ref)
+        for k, v in got.items():
+            if v > worst.get(k, (0.0, ''))[0]:
+                worst[k] = (v, cname)
+    print('MBv2 teacher-forced units, worst rel-L2 per quantity: %s' % worst)
+    assert worst['y'][0] < 1e-2, worst           # bf16 outputs: one rounding on top of the unit's own arithmetic
+    assert worst['dx'][0] < 2e-2, worst
+    assert worst['dw'][0] < 1e-2 and worst['dgamma'][0] < 1e-2 and worst['dbeta'][0] < 1e-2, worst
     ref.eval(); mine.eval()
     with torch.no_grad():
-        a, b = mine(x), ref(xq)
+        a, b = mine(x), ref(x.to(torch.bfloat16).float())
     assert _rel(a, b) < 5e-2
 
 
 def test_resnext50_grouped_against_bf16_oracle():
     """ResNeXt (32 groups, via block-diagonal dense expansion) vs the bf16-emulating oracle."""
     from convnet.pytorch_b200.models import resnext
-    ref, mine, x, y = _pair(resnext, dict(dataset='imagenet', depth=50), (3, 64, 64), 1000, steps=3, batch=8)
+    ref, mine, x, y = _pair(resnext, dict(dataset='imagenet', depth=50), (3, 64, 64), 1000, steps=3, batch=32)
     _check_against_bf16_oracle(mine, ref, x, y)
 
 
-@pytest.mark.parametrize("size,batch", [(128, 6), (160, 5), (288, 3)])
+def test_resnext101_32x4d_config_c3():
+    """BASELINE config C3's model (ResNeXt-101 32x4d: depth 101, 32 groups, C/g = 4..32): T2 against the bf16 oracle
+    at 64 px and T1 against stock torch fp32 (cuDNN grouped convolutions) at the full 224 px resolution."""
+    from convnet.pytorch_b200.models import resnext
+    ref, mine, x, y = _pair(resnext, dict(dataset='imagenet', depth=101), (3, 64, 64), 1000, steps=3, batch=32)
+    _check_against_bf16_oracle(mine, ref, x, y)
+    del ref, mine
+    ref, mine, x, y = _pair(resnext, dict(dataset='imagenet', depth=101), (3, 224, 224), 1000, steps=3, batch=32)
+    _check_step(ref, mine, x, y)
+
+
+@pytest.mark.parametrize("size,batch", [(128, 33), (160, 37), (256, 196), (288, 155)])
 def test_resnet50_mixmatch_shapes(size, batch):
-    """Mix&Match input sizes / odd batches (BASELINE config 5): no shape-specialised code path may break."""
+    """Mix&Match input sizes with odd / B+ batches (BASELINE config C5: 196 @ 256 px and 155 @ 288 px are the B+
+    batches of mixsize_config at base_device_batch=256): no shape-specialised code path may break, T1 bounds."""
     from convnet.pytorch_b200.models import resnet
-    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=50), (3, size, size), 1000, steps=2, batch=batch)
-    _check_step(ref, mine, x, y, cos_min=0.8, gcos=0.97, grel=0.3)
+    ref, mine, x, y = _pair(resnet, dict(dataset='imagenet', depth=50), (3, size, size), 1000, steps=3, batch=batch)
+    _check_step(ref, mine, x, y)
 
 
 def test_trainer_cuda_graph_replay_matches_eager():

@@ -219,9 +219,11 @@ def test_softmax_ce(B, K, ld, eps):
     logits = torch.zeros(B, ld).cuda()
     logits[:, :K] = torch.randn(B, K).cuda() * 3
     target = torch.randint(0, K, (B,)).cuda()
-    loss = torch.zeros(1).cuda()
+    loss = torch.full((1,), 77.0).cuda()          # overwritten, not accumulated
+    rows = torch.empty(B, device='cuda')
     dl = torch.empty(B, ld, device='cuda', dtype=bf16)
-    ops.softmax_ce(logits, target, K, eps, 2.0, loss, dl)
+    up = torch.full((1,), 0.5).cuda()             # upstream gradient of the loss as a device scalar
+    ops.softmax_ce(logits, target, K, eps, loss=loss, row_loss=rows, dlogits=dl, grad_scale=4.0, grad_scale_dev=up)
     lr = logits[:, :K].double().requires_grad_(True)
     ref = cross_entropy(lr, target, smooth_eps=eps if eps else None)
     gref, = torch.autograd.grad(ref, lr)
