@@ -418,7 +418,9 @@ struct WgradParams {
   int bk;               // pixels per stage
   int c_chunks;         // ceil(C / ckB)
   int total_boxes;      // taps * c_chunks
-  int boxes_per_cta;    // <= 512 / ckB and <= 8
+  int boxes_per_cta;    // <= 512 / (kt * ckB) and <= 8
+  int kt, k_groups;     // k-tiles (128 output channels each) accumulated side by side in TMEM by one CTA: the x tile is
+                        // fetched once for all of them (L2 -> SM delivery, not the tensor pipe, bounds these kernels)
   int k_tiles, col_groups, splits;
   int blocks_per_split, total_blocks;  // in units of bk pixels
   int num_stages;
@@ -469,19 +471,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   const uint32_t tmem_base = tmem_base_s;
 
   // work decomposition
-  const int tiles = p.k_tiles * p.col_groups;
+  const int tiles = p.k_groups * p.col_groups;
   const int split = blockIdx.x / tiles;
   const int tile = blockIdx.x - split * tiles;
-  const int k_tile = tile % p.k_tiles;
-  const int cgroup = tile / p.k_tiles;
-  const int k0 = k_tile * kTileM;
+  const int k_group = tile % p.k_groups;
+  const int cgroup = tile / p.k_groups;
+  const int k0 = k_group * p.kt * kTileM;
+  const int kt_valid = min(p.kt, p.k_tiles - k_group * p.kt);
   const int box0 = cgroup * p.boxes_per_cta;
   const int nboxes = min(p.boxes_per_cta, p.total_boxes - box0);
   const int blk_begin = split * p.blocks_per_split;
   const int blk_end = min(p.total_blocks, blk_begin + p.blocks_per_split);
   const int nblk = blk_end - blk_begin;
-  const int nA = min(kTileM / p.ckA, (p.K_out - k0 + p.ckA - 1) / p.ckA);  // dy boxes actually loaded
-  const uint32_t a_region = (kTileM / p.ckA) * p.boxA_bytes;
+  const uint32_t a_tile = (kTileM / p.ckA) * p.boxA_bytes;   // one k-tile of dy: 128 channels x bk pixels
+  const uint32_t a_region = p.kt * a_tile;
 
   if (nblk > 0) {
     if (warp == 0) {
@@ -489,7 +492,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         const int PQ = p.P * p.Q;
-        const uint32_t tx = nA * p.boxA_bytes + nboxes * p.boxB_bytes;
+        int nA_total = 0;
+        for (int j = 0; j < kt_valid; ++j)
+          nA_total += min(kTileM / p.ckA, (p.K_out - (k0 + j * kTileM) + p.ckA - 1) / p.ckA);
+        const uint32_t tx = nA_total * p.boxA_bytes + nboxes * p.boxB_bytes;
         for (int b = blk_begin; b < blk_end; ++b) {
           const int pix0 = b * p.bk;
           const int img = pix0 / PQ;
@@ -502,8 +508,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + a_region;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
-          for (int a = 0; a < nA; ++a)
-            tma_load_2d(&tmDy, &full_bar[stage], sa + a * p.boxA_bytes, k0 + a * p.ckA, pix0);
+          for (int j = 0; j < kt_valid; ++j) {
+            const int kj = k0 + j * kTileM;
+            const int nA = min(kTileM / p.ckA, (p.K_out - kj + p.ckA - 1) / p.ckA);   // dy boxes actually loaded
+            for (int a = 0; a < nA; ++a)
+              tma_load_2d(&tmDy, &full_bar[stage], sa + j * a_tile + a * p.boxA_bytes, kj + a * p.ckA, pix0);
+          }
           for (int x = 0; x < nboxes; ++x) {
             const int id = box0 + x;
             const int t = id / p.c_chunks;
@@ -531,20 +541,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-          const uint64_t da0 = protoA + (a_addr >> 4);
-          for (int g0 = 0; g0 < nboxes; g0 += boxes_per_mma) {
-            const int nb = min(boxes_per_mma, nboxes - g0);
-            const uint32_t idesc = make_idesc_bf16(kTileM, nb * p.ckB, 1, 1);
-            const uint64_t db0 = protoB + ((a_addr + a_region + g0 * p.boxB_bytes) >> 4);
-            const uint32_t d_tmem = tmem_base + g0 * p.ckB;
-            if (ksteps == 4) {
-              umma_bf16(d_tmem, da0, db0, idesc, b != 0 ? 1u : 0u);
-              umma_bf16(d_tmem, da0 + kincA, db0 + kincB, idesc, 1u);
-              umma_bf16(d_tmem, da0 + 2 * kincA, db0 + 2 * kincB, idesc, 1u);
-              umma_bf16(d_tmem, da0 + 3 * kincA, db0 + 3 * kincB, idesc, 1u);
-            } else {
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, da0 + k * kincA, db0 + k * kincB, idesc, (b | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < kt_valid; ++j) {
+            const uint64_t da0 = protoA + ((a_addr + j * a_tile) >> 4);
+            for (int g0 = 0; g0 < nboxes; g0 += boxes_per_mma) {
+              const int nb = min(boxes_per_mma, nboxes - g0);
+              const uint32_t idesc = make_idesc_bf16(kTileM, nb * p.ckB, 1, 1);
+              const uint64_t db0 = protoB + ((a_addr + a_region + g0 * p.boxB_bytes) >> 4);
+              const uint32_t d_tmem = tmem_base + (j * p.boxes_per_cta + g0) * p.ckB;
+              if (ksteps == 4) {
+                umma_bf16(d_tmem, da0, db0, idesc, b != 0 ? 1u : 0u);
+                umma_bf16(d_tmem, da0 + kincA, db0 + kincB, idesc, 1u);
+                umma_bf16(d_tmem, da0 + 2 * kincA, db0 + 2 * kincB, idesc, 1u);
+                umma_bf16(d_tmem, da0 + 3 * kincA, db0 + 3 * kincB, idesc, 1u);
+              } else {
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16(d_tmem, da0 + k * kincA, db0 + k * kincB, idesc, (b | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -554,49 +566,53 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       }
     } else {
       const int q = warp & 3;
-      const int k = k0 + q * 32 + lane;
-      const bool row_ok = k < p.K_out;
       mbar_wait(&acc_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      if (p.partial != nullptr) {
-        // split-K: plain stores of this CTA's fp32 tile; conv_wgrad_reduce_kernel sums the splits into dw
-        float* dst = p.partial + ((static_cast<long long>(tile) * p.splits + split) * kTileM + (q * 32 + lane)) * p.pitch;
-        const int ncols = nboxes * p.ckB;
-        for (int c0 = 0; c0 < ncols; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<float4*>(dst + c0 + 4 * i) =
-                  make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                              __uint_as_float(v[4 * i + 3]));
-          }
-        }
-      } else {
-        for (int x = 0; x < nboxes; ++x) {
-          const int id = box0 + x;
-          const int t = id / p.c_chunks;
-          const int cc = id - t * p.c_chunks;
-          const int tap = p.taps[t].b_tap;
-          const int cbase = cc * p.ckB;
-          float* dst = p.dw + (static_cast<long long>(k) * p.taps_total + tap) * p.C + cbase;
-          for (int c0 = 0; c0 < p.ckB; c0 += 16) {
+      for (int j = 0; j < kt_valid; ++j) {
+        const int k = k0 + j * kTileM + q * 32 + lane;
+        const bool row_ok = k < p.K_out;
+        const int col_j = j * p.boxes_per_cta * p.ckB;
+        if (p.partial != nullptr) {
+          // split-K: plain stores of this CTA's fp32 tile; conv_wgrad_reduce_kernel sums the splits into dw
+          float* dst = p.partial + ((static_cast<long long>(tile) * p.splits + split) * kTileM + (q * 32 + lane)) * p.pitch +
+                       col_j;
+          const int ncols = nboxes * p.ckB;
+          for (int c0 = 0; c0 < ncols; c0 += 16) {
             uint32_t v[16];
-            tmem_ld16(taddr + x * p.ckB + c0, v);
+            tmem_ld16(taddr + col_j + c0, v);
             tmem_ld_wait();
             if (row_ok) {
-              if (cbase + c0 + 16 <= p.C && (p.C & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  red_add_v4(dst + c0 + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-              } else {
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(dst + c0 + 4 * i) =
+                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                __uint_as_float(v[4 * i + 3]));
+            }
+          }
+        } else {
+          for (int x = 0; x < nboxes; ++x) {
+            const int id = box0 + x;
+            const int t = id / p.c_chunks;
+            const int cc = id - t * p.c_chunks;
+            const int tap = p.taps[t].b_tap;
+            const int cbase = cc * p.ckB;
+            float* dst = p.dw + (static_cast<long long>(k) * p.taps_total + tap) * p.C + cbase;
+            for (int c0 = 0; c0 < p.ckB; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(taddr + col_j + x * p.ckB + c0, v);
+              tmem_ld_wait();
+              if (row_ok) {
+                if (cbase + c0 + 16 <= p.C && (p.C & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (cbase + c0 + i < p.C) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+                  for (int i = 0; i < 4; ++i)
+                    red_add_v4(dst + c0 + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (cbase + c0 + i < p.C) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+                }
               }
             }
           }
@@ -618,7 +634,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 // with one thread per output the loop over up to 148 splits was a serial chain of L2 round trips.
 __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                                 int K_out, int taps, int C, int ckB, int c_chunks,
-                                                                int boxes_per_cta, int k_tiles, int splits, int pitch) {
+                                                                int boxes_per_cta, int kt, int k_groups, int splits,
+                                                                int pitch) {
   __shared__ float4 red[8][32];
   const int c4n = C >> 2;
   const long long total = static_cast<long long>(K_out) * taps * c4n;
@@ -632,11 +649,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
       tap = static_cast<int>((idx / c4n) % taps);
       k = static_cast<int>(idx / (static_cast<long long>(c4n) * taps));
       const int k_tile = k / kTileM, row = k - k_tile * kTileM;
+      const int k_group = k_tile / kt, j = k_tile - k_group * kt;
       const int cc = c / ckB;
       const int id = tap * c_chunks + cc;
       const int cgroup = id / boxes_per_cta, x = id - cgroup * boxes_per_cta;
-      const int tile = cgroup * k_tiles + k_tile;
-      const float* src = partial + ((static_cast<long long>(tile) * splits) * kTileM + row) * pitch + x * ckB + (c - cc * ckB);
+      const int tile = cgroup * k_groups + k_group;
+      const float* src = partial + ((static_cast<long long>(tile) * splits) * kTileM + row) * pitch +
+                         (j * boxes_per_cta + x) * ckB + (c - cc * ckB);
       for (int s2 = w; s2 < splits; s2 += nw) {
         const float4 v = __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(s2) * kTileM * pitch));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -999,27 +1018,41 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   p.bk = 64;  // pixels per TMA box: fewer, larger TMA requests per byte (32-pixel boxes were request-rate bound)
   p.c_chunks = (d->C + p.ckB - 1) / p.ckB;
   p.total_boxes = p.taps_total * p.c_chunks;
-  p.boxes_per_cta = 512 / p.ckB;
-  if (p.boxes_per_cta > 8) p.boxes_per_cta = 8;
-  if (p.boxes_per_cta > p.total_boxes) p.boxes_per_cta = p.total_boxes;
   p.k_tiles = (d->K + kTileM - 1) / kTileM;
+  p.boxA_bytes = p.bk * p.ckA * 2;
+  p.boxB_bytes = p.bk * p.ckB * 2;
+  // Tile shape: kt k-tiles x bpc channel boxes per CTA (kt * bpc * ckB <= 512 TMEM columns).  The kernels are bound by
+  // operand delivery from L2, so pick the shape that fetches the fewest bytes per MMA flop:
+  //   bytes per stage = kt * (dy tile) + bpc * (x box),  flops per stage ~ kt * bpc.
+  static const int kt_cap = getenv("B200_WGRAD_KT") ? atoi(getenv("B200_WGRAD_KT")) : 4;
+  double best = 1e30;
+  p.kt = 1; p.boxes_per_cta = 1;
+  for (int kt = 1; kt <= 4 && kt <= p.k_tiles && kt <= kt_cap; kt *= 2) {
+    int bpc = 512 / (kt * p.ckB);
+    if (bpc > 8) bpc = 8;
+    if (bpc > p.total_boxes) bpc = p.total_boxes;
+    if (bpc < 1) continue;
+    const double a_bytes = (double)kt * (kTileM / p.ckA) * p.boxA_bytes, b_bytes = (double)bpc * p.boxB_bytes;
+    if (a_bytes + b_bytes > 96.0 * 1024) continue;                       // at least two stages in shared memory
+    const double cost = (a_bytes + b_bytes) / ((double)kt * bpc * p.ckB);
+    if (cost < best * 0.999) { best = cost; p.kt = kt; p.boxes_per_cta = bpc; }
+  }
+  p.k_groups = (p.k_tiles + p.kt - 1) / p.kt;
   p.col_groups = (p.total_boxes + p.boxes_per_cta - 1) / p.boxes_per_cta;
   p.total_blocks = (p.M_total + p.bk - 1) / p.bk;
-  const int tiles = p.k_tiles * p.col_groups;
+  const int tiles = p.k_groups * p.col_groups;
   int splits = sm_count() / tiles;  // one wave: a CTA owns the whole TMEM, two cannot share an SM
   if (splits > p.total_blocks) splits = p.total_blocks;
   if (splits < 1) splits = 1;
   p.blocks_per_split = (p.total_blocks + splits - 1) / splits;
   p.splits = (p.total_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
-  p.boxA_bytes = p.bk * p.ckA * 2;
-  p.boxB_bytes = p.bk * p.ckB * 2;
-  p.stage_bytes = (kTileM / p.ckA) * p.boxA_bytes + p.boxes_per_cta * p.boxB_bytes;
+  p.stage_bytes = p.kt * (kTileM / p.ckA) * p.boxA_bytes + p.boxes_per_cta * p.boxB_bytes;
   p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
   p.num_stages = kSmemBudget / (int)p.stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (p.num_stages < 2) p.num_stages = 2;
   p.dw = dw;
-  p.pitch = p.boxes_per_cta * p.ckB;
+  p.pitch = p.kt * p.boxes_per_cta * p.ckB;
   p.partial = nullptr;
   if (p.splits > 1) {
     const size_t need = static_cast<size_t>(tiles) * p.splits * kTileM * p.pitch * sizeof(float);
@@ -1058,8 +1091,8 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
     long long blocks = (total + 31) / 32;
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
     conv_wgrad_reduce_kernel<<<static_cast<int>(blocks), 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, d->K, p.taps_total, d->C, p.ckB,
-                                                                          p.c_chunks, p.boxes_per_cta, p.k_tiles, p.splits,
-                                                                          p.pitch);
+                                                                          p.c_chunks, p.boxes_per_cta, p.kt, p.k_groups,
+                                                                          p.splits, p.pitch);
     B200_CHECK_LAUNCH("conv_wgrad_reduce_kernel");
   }
   return B200_OK;

@@ -139,6 +139,10 @@ class Arena(object):
             self.g32.zero_()
             self.grads_zero = True
 
+    def zero_grad_force(self):
+        self.grads_zero = False
+        self.zero_grad()
+
     def rebind_grads(self):
         for s in self.slots:
             if s.param.grad is None or s.param.grad.data_ptr() != self.g32.data_ptr() + 4 * s.offset:
@@ -212,6 +216,10 @@ class Runtime(object):
         self._fold_cache = {}
         self._want_tape = True
         self.loss_scale_inv = 1.0
+        self.grad_bucket_hook = None # Trainer (data parallel): .bucket(lo, hi, wg_stream) when g32[lo:hi) is complete,
+                                     # .finish() at the end of the backward pass
+        self._bucket_hi = None
+        self._bucket_min = int(os.environ.get('B200_BUCKET_MIN_ELEMS', 1 << 20))
         self._fused_dl = None        # bf16 dlogits handed from _FusedCE.backward to run_backward (side channel)
         self._ce_dummy = torch.zeros((), device=device, dtype=torch.float32)
         self._build()
@@ -371,6 +379,38 @@ class Runtime(object):
             torch.cuda.current_stream().wait_stream(self._wg_stream)
             self._wg_keep = []
 
+    # ---- gradient buckets for the data-parallel all-reduce ------------------------------------------------------
+    # Dense conv / fc weights sit in the arena in forward (module) order and the backward pass completes them in
+    # reverse, so "every dense weight gradient at offset >= lo is final" holds at block boundaries.  Whenever at
+    # least _bucket_min elements have become final, the hook (Trainer: an NCCL all-reduce on a communication stream)
+    # is called for that arena range while the rest of the backward pass keeps running -- the reference gets the same
+    # overlap from DistributedDataParallel's 25 MB buckets (trainer.py:79-82).  The remainder (early layers, depthwise
+    # weights, BN / bias vectors) goes out in a final call at the end of the pass.
+    def _buckets_begin(self):
+        self._bucket_hi = self.arena.group_end[0] if self.grad_bucket_hook is not None else None
+
+    def _bucket_point(self, lo, force=False):
+        """gradients of every dense weight at arena offset >= lo are complete (their wgrads are enqueued)."""
+        if self._bucket_hi is None:
+            return
+        if lo < self._bucket_hi and (force or self._bucket_hi - lo >= self._bucket_min):
+            self.grad_bucket_hook.bucket(lo, self._bucket_hi, self._wg_stream)
+            self._bucket_hi = lo
+
+    def _buckets_end(self):
+        if self._bucket_hi is None:
+            return
+        self._bucket_point(0, force=True)
+        a = self.arena
+        if a.total > a.group_end[0]:
+            self.grad_bucket_hook.bucket(a.group_end[0], a.total, None)   # depthwise weights, biases, BN affine
+        self.grad_bucket_hook.finish()
+        self._bucket_hi = None
+
+    @staticmethod
+    def _spec_lo(convs):
+        return min(c.slot.offset for c in convs)
+
     def _conv_bwd(self, u, dz, need_dx=True, residual=None):
         """wgrad into the gradient arena and (optionally) dgrad."""
         conv = u.conv
@@ -457,6 +497,33 @@ class Runtime(object):
 
     def run_backward(self, tape, dlogits, dl_bf16=None):
         raise NotImplementedError
+
+    def train_step(self, x, target, smooth_eps=0.0, upstream=None):
+        """forward + mean softmax cross-entropy (label smoothing ``smooth_eps``) + backward of one batch as a straight
+        sequence of library calls -- no autograd graph, no autograd worker thread, no ATen kernels: what Trainer runs
+        (and captures into a CUDA graph) when the criterion is the plain CrossEntropyLoss of the reference
+        (trainer.py:132-162 with utils/cross_entropy.py:20-24,46-52).  ``upstream``: optional 0-dim fp32 device tensor
+        multiplied into the gradients (loss scale x grad scale).  Gradients accumulate into the arena.
+        Returns (logits, loss), both detached."""
+        if x.device.type != 'cuda':
+            raise B200Error('B200 runtime needs CUDA inputs (no CPU fallback); got %s' % x.device)
+        if target.dtype != torch.int64 or target.dim() != 1 or target.shape[0] != x.shape[0] or not target.is_cuda:
+            raise B200Error('train_step: target must be a CUDA int64 vector with one class index per sample')
+        logits, tape = self.run_forward(x, True, True)
+        pad = tape['head']['logits_pad']
+        dev = pad.device
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        rows = torch.empty(pad.shape[0], device=dev, dtype=torch.float32)
+        dl = torch.empty(pad.shape, device=dev, dtype=torch.bfloat16)
+        up = None
+        if upstream is not None:
+            up = upstream.reshape(1)
+        ops.softmax_ce(pad, target.contiguous(), self.classes, smooth_eps, loss=loss, row_loss=rows, dlogits=dl,
+                       grad_scale_dev=up)
+        self.arena.rebind_grads()
+        self.arena.grads_zero = False
+        self.run_backward(tape, logits, dl_bf16=dl)
+        return logits, loss.view(())
 
 
 class _HeadHandle(object):
@@ -682,11 +749,15 @@ class ResNetRuntime(Runtime):
 
     def run_backward(self, tape, dlogits, dl_bf16=None):
         self._transpose_weights()
+        self._buckets_begin()
         d = self._head_bwd(tape['head'], dlogits, dl_bf16)
         for spec, saved in zip(reversed(self.blocks), reversed(tape['blocks'])):
             d = self._block_bwd(spec, saved, d)
+            convs = spec['convs'] + ([spec['down'][0]] if spec['down'] is not None else [])
+            self._bucket_point(self._spec_lo(convs))
         self._stem_bwd(tape['stem'], d)
         self._wgrad_join()
+        self._buckets_end()
 
 
 class MobileNetRuntime(Runtime):
@@ -797,6 +868,7 @@ class MobileNetRuntime(Runtime):
 
     def run_backward(self, tape, dlogits, dl_bf16=None):
         self._transpose_weights()
+        self._buckets_begin()
         d = self._head_bwd(tape['head'], dlogits, dl_bf16)
         for spec, units in zip(reversed(self.blocks), reversed(tape['blocks'])):
             skip = d if spec['add_res'] else None   # out = bn(z) + x (no activation): the skip gradient is dy itself
@@ -805,8 +877,12 @@ class MobileNetRuntime(Runtime):
                 u = units[j]
                 dz, _ = self._bn_bwd(u, d, None, act)
                 d = self._mb_conv_bwd(kind, u, dz, residual=skip if j == 0 else None)
+            dense = [c for k, c, _, _ in spec['units'] if k != 'dw']
+            if dense:
+                self._bucket_point(self._spec_lo(dense))
         self._stem_bwd(tape['stem'], d)
         self._wgrad_join()
+        self._buckets_end()
 
 
 def convert_b200(model, device=None):

@@ -113,6 +113,8 @@ class Trainer(object):
                 optimizer.fold_zero_grad(True)     # the fused SGD pass also clears the gradient arena
             if distributed and self.world_size > 1:
                 self._broadcast_initial_state()
+                if os.environ.get('B200_AR_OVERLAP', '1') != '0':
+                    self.b200.grad_bucket_hook = Trainer._GradBuckets(self.b200.arena, self.b200.device)
         elif distributed:
             if device_ids and 'cuda' in str(device):
                 self.model = nn.parallel.DistributedDataParallel(model, device_ids=device_ids,
@@ -134,11 +136,56 @@ class Trainer(object):
         arena.sync_shadow()
 
     def _allreduce_gradients(self):
-        if self.b200 is not None and self.world_size > 1:
+        """Sum of the gradient arena over the ranks (the 1/world factor is folded into the SGD kernel).  With the
+        bucketed path (default) the reduction already ran inside the backward pass -- NCCL all-reduces of arena ranges
+        on a communication stream, launched as soon as a range is final and overlapped with the remaining backward
+        kernels (inside the captured graph they are graph nodes) -- and nothing is left to do here."""
+        if self.b200 is None or self.world_size <= 1 or self.b200.grad_bucket_hook is not None:
+            return
+        from . import ops
+        g32 = self.b200.arena.g32
+        with ops._T('allreduce_nccl', 0, 4 * g32.numel()):
+            dist.all_reduce(g32)
+
+    class _GradBuckets(object):
+        """engine.Runtime.grad_bucket_hook for data-parallel runs (replaces DistributedDataParallel's bucketed reducer,
+        trainer.py:79-82 of the reference)."""
+
+        def __init__(self, arena, device):
+            self.g32 = arena.g32
+            # host tensors (gloo, CPU tests of the N > 1 logic) have no streams: the reduction is then synchronous
+            self.comm = torch.cuda.Stream(device=device) if torch.device(device).type == 'cuda' else None
+            self.launched = 0
+            self.bytes = 0
+
+        def bucket(self, lo, hi, wg_stream):
             from . import ops
-            g32 = self.b200.arena.g32
-            with ops._T('allreduce_nccl', 0, 4 * g32.numel()):
-                dist.all_reduce(g32)  # sum over ranks; the 1/world factor is folded into the SGD kernel
+            seg = self.g32[lo:hi]
+            self.launched += 1
+            self.bytes += 4 * (hi - lo)
+            if self.comm is None:
+                dist.all_reduce(seg)
+                return
+            main = torch.cuda.current_stream()
+            if ops._TIMING is not None:            # bench.py's per-class timing step: serialised on the main stream
+                if wg_stream is not None:
+                    main.wait_stream(wg_stream)
+                with ops._T('allreduce_nccl', 0, 4 * seg.numel()):
+                    dist.all_reduce(seg)
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.comm.wait_event(ev)
+            if wg_stream is not None:              # the weight gradients of this range were produced on the side stream
+                ev2 = torch.cuda.Event()
+                ev2.record(wg_stream)
+                self.comm.wait_event(ev2)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(seg)
+
+        def finish(self):
+            if self.comm is not None:
+                torch.cuda.current_stream().wait_stream(self.comm)
 
     # ------------------------------------------------------------------ step capture (B200)
     # The forward + loss + backward of one batch is ~550 kernel launches; issued eagerly from Python they cost
@@ -148,13 +195,17 @@ class Trainer(object):
     def _graph_eligible(self):
         if self.b200 is None or not self.use_graphs or self._graph_broken:
             return False
+        return self._hooks_static()
+
+    def _hooks_static(self):
+        """True when no regularizer needs to run between forward and backward (such hooks can neither be replayed from
+        a graph nor wrapped around the fused forward+loss+backward call)."""
         if self._graph_static_ok is None:
             ok = True    # dropout is fine: the mask comes from torch's graph-safe CUDA generator (philox offsets advance per replay)
             opt = self.optimizer
             for o in getattr(opt, 'optim_regime_list', [opt]):
                 reg = getattr(o, 'regularizer', None)
                 for r in getattr(reg, 'regularization_list', []):
-                    # hooks that run between forward and backward cannot be replayed from a graph
                     if type(r).pre_forward is not regularization.Regularizer.pre_forward or \
                             type(r).pre_backward is not regularization.Regularizer.pre_backward:
                         ok = False
@@ -179,6 +230,13 @@ class Trainer(object):
             try:
                 self._capture(st, inputs, target)
             except Exception as e:  # noqa: BLE001  -- keep training eagerly if capture is impossible here
+                if self.b200.grad_bucket_hook is not None:
+                    # NCCL inside the capture is the likely culprit: fall back to ONE flat all-reduce after the graph
+                    logging.warning('B200: capture with in-graph all-reduce failed (%s); retrying without overlap', e)
+                    self.b200.grad_bucket_hook = None
+                    self.b200.arena.zero_grad_force()
+                    st['seen'] = 2
+                    return None
                 logging.warning('B200: CUDA-graph capture failed (%s); continuing with eager launches', e)
                 self._graph_broken = True
                 self._graphs.clear()
@@ -202,11 +260,26 @@ class Trainer(object):
         torch.cuda.synchronize()
         n0 = lib.launch_count()
         up = self._upstream()
+        eps = self._plain_ce_eps()
         with torch.cuda.graph(graph, pool=self._graph_pool):
-            out = self.model(x_s)
-            loss = self.criterion(out, y_s)
-            torch.autograd.backward(loss, grad_tensors=[up])
+            if eps is not None:            # the whole step is library calls: nothing of autograd inside the graph
+                out, loss = self.b200.train_step(x_s, y_s, eps, up)
+            else:
+                out = self.model(x_s)
+                loss = self.criterion(out, y_s)
+                torch.autograd.backward(loss, grad_tensors=[up])
         st.update(graph=graph, x=x_s, y=y_s, out=out, loss=loss, launches=lib.launch_count() - n0)
+
+    def _plain_ce_eps(self):
+        """label-smoothing coefficient when the criterion is the reference's plain CrossEntropyLoss (class indices,
+        mean reduction, no weights / soft targets / ignore index) -- the case engine.Runtime.train_step fuses;
+        None otherwise (generic autograd path)."""
+        from .utils.cross_entropy import CrossEntropyLoss
+        c = self.criterion
+        if type(c) is CrossEntropyLoss and c.weight is None and c.smooth_dist is None and c.reduction == 'mean' \
+                and c.ignore_index < 0 and c.from_logits:
+            return float(c.smooth_eps or 0.0)
+        return None
 
     def _upstream(self):
         """d(scaled loss)/d(loss) = grad_scale * loss_scale (trainer.py:158-161 of the reference multiplies the loss)
@@ -260,6 +333,16 @@ class Trainer(object):
                     outputs.append(replayed[0])
                     total_loss += float(replayed[1])
                     continue
+            if training and self.b200 is not None and chunk_batch == 1 and not average_output and inputs.is_cuda \
+                    and self._hooks_static() and self._plain_ce_eps() is not None \
+                    and target.dtype == torch.long and target.dim() == 1:
+                # eager form of the captured step (warm-up iterations of a new shape, B200_CUDA_GRAPH=0)
+                self.optimizer.pre_forward()
+                output, loss = self.b200.train_step(inputs, target, self._plain_ce_eps(), self._upstream())
+                outputs.append(output)
+                total_loss += float(loss)
+                self.optimizer.pre_backward()
+                continue
             if training:
                 self.optimizer.pre_forward()
             output = self.model(inputs)

@@ -157,12 +157,14 @@ def test_full_size_bottleneck_at_benchmark_shape():
     torch.cuda.synchronize()
     ry, rdx = _rel(y.float().permute(0, 3, 1, 2), yr), _rel(dx.float().permute(0, 3, 1, 2), xr.grad)
     print('full-size bottleneck: y rel %.3e dx rel %.3e' % (ry, rdx))
-    assert ry < 1e-2 and rdx < 2e-2
+    # the reference is fp64 end to end (no storage emulation): T1 bounds of SURVEY.md section 8c apply -- the ideal
+    # bf16-storage pipeline itself sits at rel-L2 ~4.4e-2 on gradients after three conv+BN units
+    assert ry < 1e-2 and rdx < 8e-2
     mine = dict(model.layer1[1].named_parameters())
     for n, q in blk.named_parameters():
         c, r = _cos(mine[n].grad, q.grad), _rel(mine[n].grad, q.grad)
         print('   %-14s cos %.6f rel %.3e' % (n, c, r))
-        assert c > 0.999 and r < 3e-2, n
+        assert c > 0.998 and r < 8e-2, n
     # pixel subsample, element-wise: 2 bf16 ulp of the channel maximum on 4096 random pixels
     idx = torch.randint(0, 256 * 56 * 56, (4096,), generator=g).cuda()
     a = y.float().view(-1, 256)[idx]

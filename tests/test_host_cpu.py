@@ -130,13 +130,26 @@ def _gloo_worker(rank, world, port, ret):
         g32 = torch.full((10,), float(rank + 1))
     class _RT:
         arena = _Arena()
+        grad_bucket_hook = None
     tr.b200, tr.world_size = _RT(), world
     tr._allreduce_gradients()
+    # bucketed form (what the backward pass drives on the B200 path): ranges reduced as they become final, in
+    # reverse arena order, must add up to the same flat sum; afterwards _allreduce_gradients has nothing left to do
+    class _Arena2:
+        g32 = torch.arange(12, dtype=torch.float32) * (rank + 1)
+    hook = Trainer._GradBuckets(_Arena2, 'cpu')
+    for lo, hi in ((8, 12), (3, 8), (0, 3)):
+        hook.bucket(lo, hi, None)
+    hook.finish()
+    _RT.grad_bucket_hook = hook
+    tr._allreduce_gradients()
+    ok_buckets = bool(torch.equal(_Arena2.g32, torch.arange(12, dtype=torch.float32) * sum(range(1, world + 1)))) \
+        and hook.launched == 3 and bool(torch.all(_Arena.g32 == sum(range(1, world + 1))))
     opt = OptimRegime(models.resnet(dataset='cifar10', depth=8), [{'epoch': 0, 'optimizer': 'SGD', 'lr': 0.1}])
     opt.set_grad_unscale(4.0, world)
     ok_sum = bool(torch.all(_Arena.g32 == sum(range(1, world + 1)))) and abs(opt._inv_scale - 1.0 / (4.0 * world)) < 1e-12
     if rank == 0:
-        ret['same'], ret['sum'] = same, ok_sum
+        ret['same'], ret['sum'] = same, ok_sum and ok_buckets
     dist.destroy_process_group()
 
 
