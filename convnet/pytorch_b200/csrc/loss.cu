@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __r
                                                                 const float* __restrict__ grad_scale_dev,
                                                                 float* __restrict__ row_loss,
                                                                 __nv_bfloat16* __restrict__ dlogits) {
+  // row_loss layout: [0, B) per-sample loss, [B, 2B) number of classes scoring strictly above the target class
+  // (rank of the target: top-1 <=> 0, top-5 <=> < 5 -- utils/meters.py:59-72 of the reference, ties aside)
   __shared__ float sh[kCeThreads / 32];
   const int b = blockIdx.x;
   const float* row = logits + (long long)b * ld;
@@ -49,9 +51,16 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __r
   const int t = (int)target[b];
   const float eps_sum = eps / (float)classes;
   const float eps_nll = 1.f - eps_sum - eps;
-  if (row_loss != nullptr && threadIdx.x == 0) {
-    // sum_c lsm[c] = sx - classes*lse
-    row_loss[b] = -(eps_nll * (row[t] - lse) + eps_sum * (sx - (float)classes * lse));
+  if (row_loss != nullptr) {
+    const float xt = row[t];
+    float above = 0.f;
+    for (int c = threadIdx.x; c < classes; c += kCeThreads) above += (row[c] > xt) ? 1.f : 0.f;
+    above = block_reduce(above, false, sh);
+    if (threadIdx.x == 0) {
+      // sum_c lsm[c] = sx - classes*lse
+      row_loss[b] = -(eps_nll * (xt - lse) + eps_sum * (sx - (float)classes * lse));
+      row_loss[B + b] = above;
+    }
   }
   if (dlogits != nullptr) {
     const float gs = grad_scale * (grad_scale_dev != nullptr ? __ldg(grad_scale_dev) : 1.f) / (float)B;
@@ -66,14 +75,26 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __r
   }
 }
 
-// loss = mean_b row_loss[b]: one block, fixed summation order (bit-reproducible, no atomics, no pre-zeroed output)
+// loss[0] = mean_b row_loss[b], loss[1] / loss[2] = top-1 / top-5 precision in percent: one block, fixed summation
+// order (bit-reproducible, no atomics, no pre-zeroed output)
 __global__ void __launch_bounds__(kCeThreads) ce_mean_kernel(const float* __restrict__ row_loss, int B,
                                                              float* __restrict__ loss) {
   __shared__ float sh[kCeThreads / 32];
-  float s = 0.f;
-  for (int b = threadIdx.x; b < B; b += kCeThreads) s += row_loss[b];
+  float s = 0.f, t1 = 0.f, t5 = 0.f;
+  for (int b = threadIdx.x; b < B; b += kCeThreads) {
+    s += row_loss[b];
+    const float above = row_loss[B + b];
+    t1 += above < 0.5f ? 1.f : 0.f;
+    t5 += above < 4.5f ? 1.f : 0.f;
+  }
   s = block_reduce(s, false, sh);
-  if (threadIdx.x == 0) *loss = s / (float)B;
+  t1 = block_reduce(t1, false, sh);
+  t5 = block_reduce(t5, false, sh);
+  if (threadIdx.x == 0) {
+    loss[0] = s / (float)B;
+    loss[1] = 100.f * t1 / (float)B;
+    loss[2] = 100.f * t5 / (float)B;
+  }
 }
 
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ m, int B, int K,

@@ -48,6 +48,49 @@ __global__ void __launch_bounds__(256) input_prep_kernel(const float* __restrict
   }
 }
 
+// uint8 NHWC images (what a decoder produces) -> the same bf16 layouts, normalised on the fly:
+// value = u8 * scale[c] + bias[c]  (scale = 1 / (255 * std), bias = -mean / std: ToTensor + Normalize of the reference's
+// preprocess.py:20-24).  4x fewer host->device bytes than the fp32 NCHW batch and no separate normalisation pass.
+struct U8Norm { float scale[4], bias[4]; };
+__global__ void __launch_bounds__(256) input_prep_u8_kernel(const uint8_t* __restrict__ x, int N, int C, int H, int W,
+                                                            int Cpad, int mode, U8Norm nm,
+                                                            __nv_bfloat16* __restrict__ out) {
+  const int brd = mode == 2 ? 2 : 0;
+  const int OH = mode == 0 ? H : H / 2 + (mode == 2 ? 3 : 0), OW = mode == 0 ? W : W / 2 + (mode == 2 ? 3 : 0);
+  const long long total = (long long)N * OH * OW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % OW) - brd;
+    const int i = (int)((idx / OW) % OH) - brd;
+    const int n = (int)(idx / ((long long)OW * OH));
+    __nv_bfloat16* o = out + idx * Cpad;
+    const bool inside = mode != 2 || (i >= 0 && j >= 0 && i < H / 2 && j < W / 2);
+    const uint8_t* xi = x + (long long)n * H * W * C;
+    for (int c0 = 0; c0 < Cpad; c0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = c0 + e;
+        float val = 0.f;
+        if (mode == 0) {
+          if (ch < C) val = fmaf((float)__ldg(xi + ((long long)i * W + j) * C + ch), nm.scale[ch], nm.bias[ch]);
+        } else {
+          const int sub = ch / C, c = ch - sub * C;  // sub = dy*2+dx
+          if (sub < 4 && inside) {
+            const int dy = sub >> 1, dx = sub & 1;
+            val = fmaf((float)__ldg(xi + ((long long)(2 * i + dy) * W + (2 * j + dx)) * C + c), nm.scale[c], nm.bias[c]);
+          }
+        }
+        f[e] = val;
+      }
+      uint4 u;
+      u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+      u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(o + c0) = u;
+    }
+  }
+}
+
 // bf16 [K][T][C] -> [C][T][K]; one 32x32 tile per block, blockIdx.z = tap
 __global__ void __launch_bounds__(256) weight_transpose_kernel(const __nv_bfloat16* __restrict__ src,
                                                                __nv_bfloat16* __restrict__ dst, int K, int T, int C) {
@@ -176,6 +219,28 @@ extern "C" int b200_input_prep(const float* x, int N, int C, int H, int W, int C
   input_prep_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(x, N, C, H, W, Cpad, mode,
                                                                           (__nv_bfloat16*)out);
   B200_CHECK_LAUNCH("input_prep_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_input_prep_u8(const uint8_t* x_nhwc, int N, int C, int H, int W, int Cpad, int mode,
+                                  const float* scale_host, const float* bias_host, void* out, b200_stream_t stream) {
+  B200_REQUIRE(x_nhwc && out && scale_host && bias_host && N > 0 && C > 0 && C <= 4 && H > 0 && W > 0,
+               B200_ERR_INVALID, "input_prep_u8: bad argument (C must be 1..4)");
+  B200_REQUIRE(Cpad % 8 == 0 && Cpad >= C, B200_ERR_INVALID, "input_prep_u8: Cpad must be a multiple of 8 and >= C");
+  B200_REQUIRE(mode >= 0 && mode <= 2, B200_ERR_INVALID, "input_prep_u8: unknown mode %d", mode);
+  if (mode != 0)
+    B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && 4 * C <= Cpad, B200_ERR_UNSUPPORTED,
+                 "input_prep_u8: space-to-depth needs even H, W and 4*C <= Cpad");
+  U8Norm nm;
+  for (int c = 0; c < 4; ++c) { nm.scale[c] = c < C ? scale_host[c] : 0.f; nm.bias[c] = c < C ? bias_host[c] : 0.f; }
+  const int OH = mode == 0 ? H : H / 2 + (mode == 2 ? 3 : 0), OW = mode == 0 ? W : W / 2 + (mode == 2 ? 3 : 0);
+  const long long total = (long long)N * OH * OW;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  input_prep_u8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x_nhwc, N, C, H, W, Cpad, mode, nm,
+                                                                       (__nv_bfloat16*)out);
+  B200_CHECK_LAUNCH("input_prep_u8_kernel");
   return B200_OK;
 }
 

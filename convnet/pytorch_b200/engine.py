@@ -253,6 +253,24 @@ class Runtime(object):
     def _coeffs(self, n):
         return torch.empty(n, device=self.device, dtype=torch.float32)
 
+    # network input: the reference's contract is a normalised NCHW fp32 batch (trainer.py:116-117).  Additionally a
+    # uint8 NHWC batch [N, H, W, C] -- what an image decoder yields BEFORE ToTensor/Normalize (preprocess.py:20-24) --
+    # is accepted and normalised inside the relayout kernel (device input pipeline).
+    input_mean = (0.485, 0.456, 0.406)
+    input_std = (0.229, 0.224, 0.225)
+
+    def _input(self, x):
+        """-> (tensor, relayout function, (N, C, H, W))"""
+        if x.dtype == torch.uint8:
+            if x.dim() != 4 or x.shape[-1] > 4:
+                raise B200Error('uint8 network inputs must be NHWC [N, H, W, C<=4]; got %s' % (tuple(x.shape),))
+            N, H, W, C = x.shape
+            mean = getattr(self.model, 'input_mean', self.input_mean)
+            std = getattr(self.model, 'input_std', self.input_std)
+            return x.contiguous(), (lambda t, cpad, **kw: ops.input_prep_u8(t, cpad, mean[:C], std[:C], **kw)), (N, C, H, W)
+        N, C, H, W = x.shape
+        return x.float().contiguous(), ops.input_prep, (N, C, H, W)
+
     # ---- inference: BatchNorm folded into the convolution (reference utils/absorb_bn.py:18-48) ----------------
     # w' = w * gamma/sqrt(var+eps) per output channel, b' = beta - mean*gamma/sqrt(var+eps): one kernel computes
     # act(conv(x, w') + b' [+ residual]) -- no z tensor, no separate BN pass.  Folded weights are cached until the
@@ -504,7 +522,7 @@ class Runtime(object):
         (and captures into a CUDA graph) when the criterion is the plain CrossEntropyLoss of the reference
         (trainer.py:132-162 with utils/cross_entropy.py:20-24,46-52).  ``upstream``: optional 0-dim fp32 device tensor
         multiplied into the gradients (loss scale x grad scale).  Gradients accumulate into the arena.
-        Returns (logits, loss), both detached."""
+        Returns (logits, stats): logits detached, stats = fp32[3] device tensor {mean loss, top-1 %, top-5 %}."""
         if x.device.type != 'cuda':
             raise B200Error('B200 runtime needs CUDA inputs (no CPU fallback); got %s' % x.device)
         if target.dtype != torch.int64 or target.dim() != 1 or target.shape[0] != x.shape[0] or not target.is_cuda:
@@ -512,26 +530,26 @@ class Runtime(object):
         logits, tape = self.run_forward(x, True, True)
         pad = tape['head']['logits_pad']
         dev = pad.device
-        loss = torch.empty(1, device=dev, dtype=torch.float32)
-        rows = torch.empty(pad.shape[0], device=dev, dtype=torch.float32)
+        stats = torch.empty(3, device=dev, dtype=torch.float32)
+        rows = torch.empty(2 * pad.shape[0], device=dev, dtype=torch.float32)
         dl = torch.empty(pad.shape, device=dev, dtype=torch.bfloat16)
         up = None
         if upstream is not None:
             up = upstream.reshape(1)
-        ops.softmax_ce(pad, target.contiguous(), self.classes, smooth_eps, loss=loss, row_loss=rows, dlogits=dl,
+        ops.softmax_ce(pad, target.contiguous(), self.classes, smooth_eps, loss=stats, row_loss=rows, dlogits=dl,
                        grad_scale_dev=up)
         self.arena.rebind_grads()
         self.arena.grads_zero = False
         self.run_backward(tape, logits, dl_bf16=dl)
-        return logits, loss.view(())
+        return logits, stats
 
 
 class _HeadHandle(object):
     """Tag on the logits of a taped forward: the padded fp32 logits storage + the runtime that produced them."""
-    __slots__ = ('rt', 'logits_pad')
+    __slots__ = ('rt', 'logits_pad', 'stats')
 
     def __init__(self, rt, logits_pad):
-        self.rt, self.logits_pad = rt, logits_pad
+        self.rt, self.logits_pad, self.stats = rt, logits_pad, None
 
     def loss(self, logits, target, smooth_eps=0.0):
         return _FusedCE.apply(logits, target, float(smooth_eps or 0.0), self)
@@ -549,12 +567,13 @@ class _FusedCE(torch.autograd.Function):
                 target.shape != (pad.shape[0],) or target.dtype != torch.int64 or not target.is_cuda:
             raise B200Error('fused cross-entropy: logits/target do not belong to this forward pass')
         target = target.contiguous()
-        loss = torch.empty(1, device=pad.device, dtype=torch.float32)
-        rows = torch.empty(pad.shape[0], device=pad.device, dtype=torch.float32)
-        ops.softmax_ce(pad, target, rt.classes, eps, loss=loss, row_loss=rows)
+        stats = torch.empty(3, device=pad.device, dtype=torch.float32)          # loss, top-1 %, top-5 %
+        rows = torch.empty(2 * pad.shape[0], device=pad.device, dtype=torch.float32)
+        ops.softmax_ce(pad, target, rt.classes, eps, loss=stats, row_loss=rows)
         ctx.head, ctx.eps = head, eps
         ctx.save_for_backward(target)
-        return loss.view(())
+        head.stats = stats
+        return stats[0]
 
     @staticmethod
     def backward(ctx, gout):
@@ -639,9 +658,8 @@ class ResNetRuntime(Runtime):
 
     # ---- stem ---------------------------------------------------------------------------------------
     def _stem_fwd(self, x, training):
-        N, Cin, H, W = x.shape
+        x, prep, (N, Cin, H, W) = self._input(x)
         K = self.stem_conv.out_channels
-        x = x.float().contiguous()
         st = {}
         if self.imagenet_stem:
             ws = torch.empty((K, 16, 16), device=self.device, dtype=torch.bfloat16)
@@ -651,7 +669,7 @@ class ResNetRuntime(Runtime):
                 # 7x7/s2 -> space-to-depth 4x4/s1 on 16 channels -> 4x1 on "wide pixels": 4 neighbouring 32-byte
                 # pixels of the zero-bordered tensor are read as ONE 64-channel (128 B) pixel, so every tap row is a
                 # full 128B-swizzle TMA tile (4 loads per tile instead of 16 quarter-width ones).
-                xs = ops.input_prep(x, 16, s2d=True, border=True)      # [N, Hs+3, Ws+3, 16], data at (+2,+2)
+                xs = prep(x, 16, s2d=True, border=True)                # [N, Hs+3, Ws+3, 16], data at (+2,+2)
                 desc = ops.make_desc(N, Hs + 3, Ws, 64, K, 4, 1, 1, 0, P=Hs, Q=Ws,
                                      x_strides=(16, (Ws + 3) * 16, (Hs + 3) * (Ws + 3) * 16), algo_macs=K * 49 * Cin)
                 st['wgrad_desc'] = desc
@@ -662,10 +680,10 @@ class ResNetRuntime(Runtime):
                     if HALO_STEM_WGRAD:
                         st['wgrad_desc'] = desc
             else:
-                xs = ops.input_prep(x, 16, s2d=True)                   # [N, H/2, W/2, 16]
+                xs = prep(x, 16, s2d=True)                             # [N, H/2, W/2, 16]
                 desc = ops.make_desc(N, Hs, Ws, 16, K, 4, 4, 1, 2, P=Hs, Q=Ws, algo_macs=K * 49 * Cin)
         else:
-            xs = ops.input_prep(x, 16, s2d=False)
+            xs = prep(x, 16, s2d=False)
             ws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.bfloat16)
             ws[:, :, :Cin].copy_(self.stem_w32.view(K, 9, Cin))       # 432-element pad+cast of the 3-channel stem
             desc = ops.make_desc(N, H, W, 16, K, 3, 3, 1, 1, algo_macs=K * 9 * Cin)
@@ -823,9 +841,9 @@ class MobileNetRuntime(Runtime):
         return self._conv_bwd(u, dz, need_dx=need_dx, residual=residual)
 
     def _stem_fwd(self, x, training):
-        N, Cin, H, W = x.shape
+        x, prep, (N, Cin, H, W) = self._input(x)
         K = self.stem_conv.out_channels
-        xs = ops.input_prep(x.float().contiguous(), 16, s2d=False)
+        xs = prep(x, 16, s2d=False)
         ws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.bfloat16)
         ws[:, :, :Cin].copy_(self.stem_w32.view(K, 9, Cin))
         st, pad = self.stem_conv.stride[0], self.stem_conv.padding[0]

@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200_avgpool_fwd": [_vp, _i, _i, _i, _vp, _vp],
     "b200_avgpool_bwd": [_vp, _i, _i, _i, _vp, _vp],
     "b200_input_prep": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "b200_input_prep_u8": [_vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                           _vp, _vp],
     "b200_weight_transpose": [_vp, _vp, _i, _i, _i, _vp],
     "b200_weight_transpose_batched": [_vp, _vp, _vp, _i, _i, _vp],
     "b200_stem_weight_to_s2d": [_vp, _i, _i, _i, _vp, _vp],

@@ -310,6 +310,23 @@ def input_prep(x_nchw, cpad, s2d=False, border=False):
     return out
 
 
+def input_prep_u8(x_nhwc_u8, cpad, mean, std, s2d=False, border=False):
+    """uint8 NHWC [N,H,W,C] -> the layouts of input_prep, normalised as (u8/255 - mean)/std in the same pass."""
+    _chk(x_nhwc_u8, torch.uint8, "x")
+    N, H, W, C = x_nhwc_u8.shape
+    if s2d and border:
+        shape = (N, H // 2 + 3, W // 2 + 3, cpad)
+    else:
+        shape = (N, H // 2, W // 2, cpad) if s2d else (N, H, W, cpad)
+    out = torch.empty(shape, device=x_nhwc_u8.device, dtype=bf16)
+    scale = (ctypes.c_float * C)(*[1.0 / (255.0 * float(s)) for s in std])
+    bias = (ctypes.c_float * C)(*[-float(m) / float(s) for m, s in zip(mean, std)])
+    with _T('input_prep', 0, x_nhwc_u8.numel() + 2 * out.numel()):
+        _l.check(_l.load().b200_input_prep_u8(x_nhwc_u8.data_ptr(), N, C, H, W, cpad, (2 if border else 1) if s2d else 0,
+                                              scale, bias, out.data_ptr(), _stream()), "b200_input_prep_u8")
+    return out
+
+
 def weight_transpose(w, out=None):
     """bf16 [K,T,C] -> [C,T,K]."""
     K, T, C = w.shape
@@ -379,8 +396,11 @@ def cast_bf16(src, dst):
 # ------------------------------------------------------------------------------------ loss / optimizer
 def softmax_ce(logits, target, classes, smooth_eps, loss=None, row_loss=None, dlogits=None, grad_scale=1.0,
                grad_scale_dev=None):
-    """logits fp32 [B, ld] (ld >= classes), target int64 [B].  loss (+ row_loss [B] scratch): mean loss, overwritten;
-    dlogits bf16 [B, ld] = grad_scale * (*grad_scale_dev) / B * dloss/dlogits (pad columns zeroed)."""
+    """logits fp32 [B, ld] (ld >= classes), target int64 [B].  loss fp32[3] (+ row_loss fp32[2B] scratch): mean loss,
+    top-1 %, top-5 % -- overwritten; dlogits bf16 [B, ld] = grad_scale * (*grad_scale_dev) / B * dloss/dlogits (pad
+    columns zeroed)."""
+    if loss is not None and (loss.numel() < 3 or row_loss is None or row_loss.numel() < 2 * logits.shape[0]):
+        raise _l.B200Error("softmax_ce: loss needs 3 floats and row_loss 2*B floats")
     B, ld = logits.shape
     _chk(logits, torch.float32, "logits"); _chk(target, torch.int64, "target"); _chk(dlogits, bf16, "dlogits")
     _chk(loss, torch.float32, "loss"); _chk(row_loss, torch.float32, "row_loss")

@@ -60,7 +60,8 @@ def _cuda_prefetch(loader, device, dtype):
     pending = None
     for inputs, target in loader:
         with torch.cuda.stream(copy_stream):
-            nxt_x = inputs.to(device, dtype=dtype, non_blocking=True)
+            # uint8 image batches stay uint8 (normalised by the stem's relayout kernel): 4x fewer bytes over PCIe
+            nxt_x = inputs.to(device, dtype=None if inputs.dtype == torch.uint8 else dtype, non_blocking=True)
             nxt_y = target.to(device, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
@@ -214,7 +215,8 @@ class Trainer(object):
 
     def graphed_forward_backward(self, inputs, target):
         """Forward + criterion + backward of one device-resident batch through a captured CUDA graph.
-        Returns (logits, loss) as detached tensors, or None when this call has to run eagerly (warm-up steps of
+        Returns (logits, loss, stats) -- detached device tensors; stats = fp32[3] {loss, top-1 %, top-5 %} when the fused
+        loss kernel computed them, else None -- or None when this call has to run eagerly (warm-up steps of
         a new shape, unsupported configuration).  Gradients land in the arena exactly as in the eager path."""
         if not self._graph_eligible() or not inputs.is_cuda:
             return None
@@ -247,7 +249,7 @@ class Trainer(object):
         st['graph'].replay()
         self.graph_replays += 1
         self.graph_replayed_launches += st['launches']
-        return st['out'].detach(), st['loss'].detach()
+        return st['out'].detach(), st['loss'].detach(), st['stats']
 
     def _capture(self, st, inputs, target):
         from . import lib
@@ -262,13 +264,15 @@ class Trainer(object):
         up = self._upstream()
         eps = self._plain_ce_eps()
         with torch.cuda.graph(graph, pool=self._graph_pool):
+            stats = None
             if eps is not None:            # the whole step is library calls: nothing of autograd inside the graph
-                out, loss = self.b200.train_step(x_s, y_s, eps, up)
+                out, stats = self.b200.train_step(x_s, y_s, eps, up)
+                loss = stats[0]
             else:
                 out = self.model(x_s)
                 loss = self.criterion(out, y_s)
                 torch.autograd.backward(loss, grad_tensors=[up])
-        st.update(graph=graph, x=x_s, y=y_s, out=out, loss=loss, launches=lib.launch_count() - n0)
+        st.update(graph=graph, x=x_s, y=y_s, out=out, loss=loss, stats=stats, launches=lib.launch_count() - n0)
 
     def _plain_ce_eps(self):
         """label-smoothing coefficient when the criterion is the reference's plain CrossEntropyLoss (class indices,
@@ -318,7 +322,10 @@ class Trainer(object):
         return clip_grad_norm_(self.model.parameters(), float('inf'))
 
     def _step(self, inputs_batch, target_batch, training=False, average_output=False, chunk_batch=1):
-        outputs, total_loss, grad = [], 0, None
+        """-> (outputs, loss, grad norm or None).  ``loss`` is a float, or -- on the fused B200 path -- the fp32[3] device
+        tensor {loss, top-1 %, top-5 %} of the loss kernel, which Trainer.forward reads back asynchronously
+        (the reference synchronises three times per step here: trainer.py:153,226-227)."""
+        outputs, total_loss, grad, stats = [], 0, None, None
         if training:
             self.optimizer.zero_grad()
             self.optimizer.update(self.epoch, self.training_steps)
@@ -326,21 +333,26 @@ class Trainer(object):
         chunks = zip(inputs_batch.chunk(chunk_batch, dim=0), target_batch.chunk(chunk_batch, dim=0))
         for i, (inputs, target) in enumerate(chunks):
             target = target.to(self.device, non_blocking=True)
-            inputs = inputs.to(self.device, dtype=self._input_dtype(), non_blocking=True)
+            if self.b200 is not None and inputs.dtype == torch.uint8:
+                inputs = inputs.to(self.device, non_blocking=True)
+            else:
+                inputs = inputs.to(self.device, dtype=self._input_dtype(), non_blocking=True)
             if training and chunk_batch == 1 and not average_output:
                 replayed = self.graphed_forward_backward(inputs, target)
                 if replayed is not None:
                     outputs.append(replayed[0])
-                    total_loss += float(replayed[1])
+                    if replayed[2] is not None:
+                        stats = replayed[2]
+                    else:
+                        total_loss += float(replayed[1])
                     continue
             if training and self.b200 is not None and chunk_batch == 1 and not average_output and inputs.is_cuda \
                     and self._hooks_static() and self._plain_ce_eps() is not None \
                     and target.dtype == torch.long and target.dim() == 1:
                 # eager form of the captured step (warm-up iterations of a new shape, B200_CUDA_GRAPH=0)
                 self.optimizer.pre_forward()
-                output, loss = self.b200.train_step(inputs, target, self._plain_ce_eps(), self._upstream())
+                output, stats = self.b200.train_step(inputs, target, self._plain_ce_eps(), self._upstream())
                 outputs.append(output)
-                total_loss += float(loss)
                 self.optimizer.pre_backward()
                 continue
             if training:
@@ -391,7 +403,7 @@ class Trainer(object):
                 self.optimizer.step()
             self.training_steps += 1
 
-        return torch.cat(outputs, dim=0), total_loss, grad
+        return (outputs[0] if len(outputs) == 1 else torch.cat(outputs, dim=0)), (stats if stats is not None else total_loss), grad
 
     # ------------------------------------------------------------------ epoch loop
     def forward(self, data_loader, num_steps=None, training=False, average_output=False, chunk_batch=1):
@@ -413,6 +425,21 @@ class Trainer(object):
         tick = time.time()
         batches = _cuda_prefetch(data_loader, self.device, self._input_dtype()) \
             if (self.b200 is not None and chunk_batch == 1) else data_loader
+        # lazy meters (B200 fused path): the step's {loss, prec1, prec5} come from the loss kernel as one device
+        # tensor; it is copied to pinned host memory asynchronously every step and only awaited when a log line is
+        # due, the ring is full or the loop ends -- no host synchronisation inside a step
+        pending, ring = [], 8
+        pinned = None
+
+        def drain(keep=0):
+            while len(pending) > keep:
+                slot, ev, n = pending.pop(0)
+                ev.synchronize()
+                v = pinned[slot]
+                meters['loss'].update(float(v[0]), n)
+                meters['prec1'].update(float(v[1]), n)
+                meters['prec5'].update(float(v[2]), n)
+
         for i, (inputs, target) in enumerate(batches):
             duplicates = inputs.dim() > 4  # B x D x C x H x W
             if training and duplicates and self.adapt_grad_norm is not None and i % self.adapt_grad_norm == 0:
@@ -428,12 +455,25 @@ class Trainer(object):
                                                      expand_target=not average_output)
             output, loss, grad = self._step(inputs, target, training=training, average_output=average_output,
                                             chunk_batch=chunk_batch)
-            target_dev = target.to(output.device)
-            prec1, prec5 = accuracy(output, target_dev, topk=(1, 5))
             n = inputs.size(0)
-            meters['loss'].update(float(loss), n)
-            meters['prec1'].update(float(prec1), n)
-            meters['prec5'].update(float(prec5), n)
+            if torch.is_tensor(loss):              # fused statistics: asynchronous read-back
+                if pinned is None:
+                    pinned = torch.empty((ring, 3), dtype=torch.float32).pin_memory()
+                drain(keep=ring - 1)
+                slot = i % ring
+                pinned[slot].copy_(loss, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending.append((slot, ev, n))
+                if i % self.print_freq == 0 or i == n_batches - 1:
+                    drain()
+            else:
+                drain()
+                target_dev = target.to(output.device)
+                prec1, prec5 = accuracy(output, target_dev, topk=(1, 5))
+                meters['loss'].update(float(loss), n)
+                meters['prec1'].update(float(prec1), n)
+                meters['prec5'].update(float(prec5), n)
             if grad is not None:
                 meters['grad'].update(float(grad), n)
             meters['step'].update(time.time() - tick)
@@ -452,6 +492,7 @@ class Trainer(object):
                 logging.info(msg)
             if num_steps is not None and i >= num_steps:  # (sic) the reference runs num_steps+1 iterations
                 break
+        drain()
         return summary()
 
     def train(self, data_loader, average_output=False, chunk_batch=1):

@@ -140,6 +140,11 @@ int b200_avgpool_bwd(const void* dy, int N, int HW, int C, void* dx, b200_stream
  * mode 2: mode 1 with a physical zero border: out[N, H/2+3, W/2+3, Cpad], data at (+2,+2) -- the 4x4/s1
  *         stem conv (pad 2 low, 1 high) then needs no out-of-bounds handling and can read "wide pixels". */
 int b200_input_prep(const float* x_nchw, int N, int C, int H, int W, int Cpad, int mode, void* out, b200_stream_t stream);
+/* the same three layouts from uint8 NHWC images [N][H][W][C] (C <= 4), normalised on the fly:
+ * value = u8 * scale[c] + bias[c] with scale = 1/(255*std), bias = -mean/std -- ToTensor + Normalize of the reference's
+ * preprocess.py:20-24 fused into the relayout.  scale_host / bias_host: HOST arrays [C]. */
+int b200_input_prep_u8(const uint8_t* x_nhwc, int N, int C, int H, int W, int Cpad, int mode, const float* scale_host,
+                       const float* bias_host, void* out, b200_stream_t stream);
 /* bf16 [K][T][C] -> bf16 [C][T][K] (dgrad weight layout), multi-tensor: n tensors described by
  * device arrays. */
 int b200_weight_transpose(const void* src, void* dst, int K, int T, int C, b200_stream_t stream);
@@ -161,8 +166,9 @@ int b200_group_wgrad_extract(const float* dw_dense, int K, int T, int C, int gro
 /* ---- loss (csrc/loss.cu) ----------------------------------------------------------------------
  * replaces utils/cross_entropy.py:14-67 (F.cross_entropy / label smoothing) forward+backward.
  * logits/dlogits rows have pitch ld >= classes (columns [classes, ld) are padding: ignored on read,
- * zeroed in dlogits).  loss != NULL: row_loss[B] (scratch) receives the per-sample losses and *loss (fp32, device,
- * overwritten) their mean, summed in a fixed order.  dlogits != NULL: dlogits (bf16) = grad_scale *
+ * zeroed in dlogits).  loss != NULL: loss is fp32[3] (device, overwritten): {mean loss, top-1 %, top-5 %} -- the
+ * meters of Trainer.forward (trainer.py:224-227, utils/meters.py:59-72: rank of the target class, ties aside) --
+ * summed in a fixed order from row_loss (scratch, fp32[2*B]: per-sample loss, per-sample rank of the target).  dlogits != NULL: dlogits (bf16) = grad_scale *
  * (*grad_scale_dev if non-NULL) / B * dloss_i/dlogits -- the device scalar is the upstream gradient of the loss
  * (loss scaling, trainer.py:158-161) so that no host value is baked into a captured graph. */
 int b200_softmax_ce(const float* logits, const long long* target, int B, int classes, int ld, float smooth_eps,

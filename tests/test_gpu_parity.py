@@ -213,3 +213,93 @@ def test_eval_mode_forward_carries_no_autograd_history():
     assert not out.requires_grad
     with pytest.raises(RuntimeError):
         F.cross_entropy(out, y).backward()
+
+
+def test_uint8_input_pipeline_matches_normalised_fp32():
+    """(f2) uint8 NHWC network input, normalised inside the stem's relayout kernel, vs the reference contract -- the
+    same images as a normalised fp32 NCHW batch ((u8/255 - mean)/std, preprocess.py:20-24): identical logits up to the
+    bf16 rounding of the input (ImageNet stem: space-to-depth layouts; CIFAR stem: padded NHWC)."""
+    from convnet.pytorch_b200.models import resnet
+    from convnet.pytorch_b200.engine import convert_b200
+    for cfg, size in ((dict(dataset='imagenet', depth=18), 64), (dict(dataset='cifar10', depth=20), 32)):
+        torch.manual_seed(123)
+        m = convert_b200(resnet(**cfg), 'cuda').train()
+        g = torch.Generator().manual_seed(2)
+        u8 = torch.randint(0, 256, (32, size, size, 3), generator=g, dtype=torch.uint8)
+        mean = torch.tensor(m._b200.input_mean).view(1, 3, 1, 1)
+        std = torch.tensor(m._b200.input_std).view(1, 3, 1, 1)
+        xf = (u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+        with torch.no_grad():
+            a = m(u8.cuda())
+            b = m(xf.cuda())
+        r = _rel(a, b)
+        print('uint8 input vs fp32 (%s): logits rel %.3e' % (cfg['dataset'], r))
+        assert r < 5e-3
+
+
+def test_lazy_meters_match_torch_accuracy():
+    """Trainer.train on the fused path reads {loss, prec1, prec5} from the loss kernel asynchronously; the averages must
+    equal the reference's per-step float(loss) / accuracy(output, target) meters (trainer.py:224-227,
+    utils/meters.py:59-72) computed with torch on the same logits."""
+    from convnet.pytorch_b200.models import resnet
+    from convnet.pytorch_b200.engine import convert_b200
+    from convnet.pytorch_b200.trainer import Trainer
+    from convnet.pytorch_b200.utils.optim import OptimRegime
+    from convnet.pytorch_b200.utils.cross_entropy import CrossEntropyLoss
+    from convnet.pytorch_b200.utils.meters import accuracy
+    torch.manual_seed(123)
+    model = convert_b200(resnet(dataset='cifar10', depth=20), 'cuda')
+    tr = Trainer(model, CrossEntropyLoss().cuda(), OptimRegime(model, model.regime), device='cuda', print_freq=3)
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(64, 3, 32, 32, generator=g), torch.randint(0, 10, (64,), generator=g)) for _ in range(12)]
+    seen = []
+    orig = tr._step
+
+    def spy(inputs, target, **kw):
+        out, loss, grad = orig(inputs, target, **kw)
+        p1, p5 = accuracy(out.float(), target.cuda(), topk=(1, 5))
+        lo = torch.nn.functional.cross_entropy(out.float(), target.cuda())
+        seen.append((float(lo), float(p1), float(p5), torch.is_tensor(loss)))
+        return out, loss, grad
+    tr._step = spy
+    res = tr.train(batches)
+    assert all(s[3] for s in seen), 'fused statistics were not used'
+    for k, j in (('loss', 0), ('prec1', 1), ('prec5', 2)):
+        want = sum(s[j] for s in seen) / len(seen)
+        assert abs(res[k] - want) < 1e-3 * max(1.0, abs(want)), (k, res[k], want)
+
+
+def test_evaluate_cli_on_the_kernel_path(tmp_path):
+    """(f1) evaluate.py on the B200 path: --absorb-bn runs the conv kernels with BatchNorm folded into weights + bias
+    (one launch per conv+BN+ReLU unit) and must reproduce the unfolded evaluation; --calibrate-bn re-estimates the
+    running statistics with cumulative momentum through the training-mode statistics kernels (trainer.py:277-285)."""
+    import os
+    from convnet.pytorch_b200 import evaluate as ev
+    from convnet.pytorch_b200.models import resnet
+    torch.manual_seed(123)
+    m = resnet(dataset='cifar10', depth=20)
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(64, 3, 32, 32, generator=g), torch.randint(0, 10, (64,), generator=g)
+    opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
+    m.train()
+    for _ in range(5):                                    # leave the vacuous init, move the running statistics
+        opt.zero_grad(); F.cross_entropy(m(x), y).backward(); opt.step()
+    ck = str(tmp_path / 'ck.pth.tar')
+    torch.save({'epoch': 1, 'model': 'resnet', 'config': "{'depth': 20}", 'state_dict': m.state_dict()}, ck)
+    os.environ['B200_SYNTHETIC_LENGTH'] = '256'
+    try:
+        common = [ck, '--dataset', 'synthetic_cifar10', '-b', '64', '--workers', '0', '--b200', 'on']
+        base = ev.main(common)
+        absorbed = ev.main(common + ['--absorb-bn'])
+        calib = ev.main(common + ['--absorb-bn', '--calibrate-bn', '--calibrate-steps', '3'])
+        m.eval()
+        ref = ev.main([ck, '--dataset', 'synthetic_cifar10', '-b', '64', '--workers', '0', '--b200', 'off',
+                       '--device', 'cuda'])
+    finally:
+        del os.environ['B200_SYNTHETIC_LENGTH']
+    print('evaluate: unfolded %s | folded %s | calibrated %s | torch %s' % (base['loss'], absorbed['loss'],
+                                                                          calib['loss'], ref['loss']))
+    assert abs(base['loss'] - absorbed['loss']) < 2e-2 * max(1.0, base['loss'])
+    assert abs(base['loss'] - ref['loss']) < 2e-2 * max(1.0, ref['loss'])
+    assert abs(base['prec1'] - ref['prec1']) <= 2.0 and abs(absorbed['prec1'] - ref['prec1']) <= 2.0
+    assert calib['loss'] > 0 and calib['loss'] == calib['loss']

@@ -178,3 +178,25 @@ def test_cli_cpu_plumbing_run(tmp_path):
     assert len(rows) == 1 and float(rows[0]['training loss']) > 0 and 0 <= float(rows[0]['validation prec1']) <= 100
     ck = torch.load(out / 'checkpoint.pth.tar', map_location='cpu', weights_only=False)
     assert ck['epoch'] == 1 and 'state_dict' in ck and any(k.endswith('conv1.weight') for k in ck['state_dict'])
+
+
+def test_evaluate_cli_cpu(tmp_path):
+    """evaluate.py of the reference (evaluate.py:101-193): checkpoint -> [--absorb-bn] [--calibrate-bn] [--avg-out]
+    -> validate.  CPU / torch-module form; absorbing BatchNorm must not change the metrics."""
+    from convnet.pytorch_b200 import main as cli
+    from convnet.pytorch_b200 import evaluate as ev
+    cli.main(['--model', 'resnet', '--model-config', "{'depth': 8}", '--dataset', 'synthetic_cifar10',
+              '--device', 'cpu', '-b', '16', '--epochs', '1', '--max-steps', '2', '--workers', '0',
+              '--results-dir', str(tmp_path), '--save', 'run'])
+    ck = str(tmp_path / 'run' / 'checkpoint.pth.tar')
+    os.environ['B200_SYNTHETIC_LENGTH'] = '64'
+    try:
+        base = ev.main([ck, '--dataset', 'synthetic_cifar10', '--device', 'cpu', '-b', '16', '--workers', '0'])
+        absorbed = ev.main([ck, '--dataset', 'synthetic_cifar10', '--device', 'cpu', '-b', '16', '--workers', '0',
+                            '--absorb-bn'])
+        both = ev.main([ck, '--dataset', 'synthetic_cifar10', '--device', 'cpu', '-b', '16', '--workers', '0',
+                        '--absorb-bn', '--calibrate-bn', '--calibrate-steps', '2', '--avg-out', '--duplicates', '2'])
+    finally:
+        del os.environ['B200_SYNTHETIC_LENGTH']
+    assert abs(base['loss'] - absorbed['loss']) < 1e-4 * max(1.0, base['loss']) and base['prec1'] == absorbed['prec1']
+    assert both['loss'] > 0 and 0 <= both['prec1'] <= 100
