@@ -428,8 +428,10 @@ struct WgradParams {
   float* dw;
   int plain_x;           // 1: x is a dense [M_total, C] matrix (1x1 stride 1): tiled TMA instead of im2col
   float* partial;        // split-K partial tiles [tile][split][128][pitch] (nullptr: splits == 1, add into dw)
-  int pitch;             // boxes_per_cta * ckB
-  TapEntry taps[kMaxTaps];
+  int pitch;             // kt * boxes_per_cta * ckB
+  int S_filter;          // filter width: tap t = (r, s) = (t / S, t % S) gives the im2col offsets {s, r}.  Computed, not
+                         // read from a table: ptxas 12.9 (sm_100a) mis-split a 32-bit {off_w, off_h} word loaded through
+                         // the uniform datapath (LDCU + UPRMT on a stale register) -- wrong off_h for every tap row > 0
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -492,38 +494,53 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         const int PQ = p.P * p.Q;
+        // everything that does not depend on the pixel block is computed once: the producer thread's issue rate bounds
+        // the HBM-bound layers (one TMA request per 8 KB box)
+        int nA_j[4];
         int nA_total = 0;
-        for (int j = 0; j < kt_valid; ++j)
-          nA_total += min(kTileM / p.ckA, (p.K_out - (k0 + j * kTileM) + p.ckA - 1) / p.ckA);
+        for (int j = 0; j < 4; ++j) {
+          nA_j[j] = j < kt_valid ? min(kTileM / p.ckA, (p.K_out - (k0 + j * kTileM) + p.ckA - 1) / p.ckA) : 0;
+          nA_total += nA_j[j];
+        }
+        int box_c[8];
+        uint16_t box_w[8], box_h[8];
+        for (int x = 0; x < 8; ++x) {
+          const int id = box0 + min(x, nboxes - 1);
+          const int t = id / p.c_chunks;
+          const int th = t / p.S_filter;
+          box_c[x] = (id - t * p.c_chunks) * p.ckB;
+          box_w[x] = static_cast<uint16_t>(t - th * p.S_filter);
+          box_h[x] = static_cast<uint16_t>(th);
+        }
         const uint32_t tx = nA_total * p.boxA_bytes + nboxes * p.boxB_bytes;
         for (int b = blk_begin; b < blk_end; ++b) {
           const int pix0 = b * p.bk;
-          const int img = pix0 / PQ;
-          const int rem = pix0 - img * PQ;
-          const int pi = rem / p.Q;
-          const int pj = rem - pi * p.Q;
-          const int base_w = pj * p.trav + p.lower_w;
-          const int base_h = pi * p.trav + p.lower_h;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + a_region;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
-          for (int j = 0; j < kt_valid; ++j) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
             const int kj = k0 + j * kTileM;
-            const int nA = min(kTileM / p.ckA, (p.K_out - kj + p.ckA - 1) / p.ckA);   // dy boxes actually loaded
-            for (int a = 0; a < nA; ++a)
+            for (int a = 0; a < nA_j[j]; ++a)      // dy boxes actually present (K_out tail)
               tma_load_2d(&tmDy, &full_bar[stage], sa + j * a_tile + a * p.boxA_bytes, kj + a * p.ckA, pix0);
           }
-          for (int x = 0; x < nboxes; ++x) {
-            const int id = box0 + x;
-            const int t = id / p.c_chunks;
-            const int cc = id - t * p.c_chunks;
-            const TapEntry te = p.taps[t];
-            if (p.plain_x)
-              tma_load_2d(&tmX, &full_bar[stage], sb + x * p.boxB_bytes, cc * p.ckB, pix0);
-            else
-              tma_load_im2col_4d(&tmX, &full_bar[stage], sb + x * p.boxB_bytes, cc * p.ckB, base_w, base_h, img,
-                                 te.off_w, te.off_h);
+          if (p.plain_x) {
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+              if (x < nboxes) tma_load_2d(&tmX, &full_bar[stage], sb + x * p.boxB_bytes, box_c[x], pix0);
+          } else {
+            const int img = pix0 / PQ;
+            const int rem = pix0 - img * PQ;
+            const int pi = rem / p.Q;
+            const int pj = rem - pi * p.Q;
+            const int base_w = pj * p.trav + p.lower_w;
+            const int base_h = pi * p.trav + p.lower_h;
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+              if (x < nboxes)
+                tma_load_im2col_4d(&tmX, &full_bar[stage], sb + x * p.boxB_bytes, box_c[x], base_w, base_h, img, box_w[x],
+                                   box_h[x]);
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -537,26 +554,42 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         const uint32_t kincA = (16u * p.ckA * 2) >> 4, kincB = (16u * p.ckB * 2) >> 4;  // 16 pixel rows per K step
         const int boxes_per_mma = min(8, 256 / p.ckB);
         const int ksteps = p.bk / 16;
+        // the issuing thread is latency-bound per instruction: the (k-tile, box group) list of one stage -- descriptor
+        // offsets, TMEM column, instruction descriptor -- is built once
+        // slot (j, gi): k-tile j, box group gi (at most 2 groups of boxes_per_mma boxes); statically indexed -> registers
+        uint32_t g_da[8], g_db[8], g_tm[8], g_id[8];
+        bool g_on[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const int g0 = gi * boxes_per_mma;
+            const int nb = min(boxes_per_mma, nboxes - g0);
+            g_on[j * 2 + gi] = j < kt_valid && g0 < nboxes;
+            g_da[j * 2 + gi] = (j * a_tile) >> 4;
+            g_db[j * 2 + gi] = (a_region + g0 * p.boxB_bytes) >> 4;
+            g_tm[j * 2 + gi] = tmem_base + (j * p.boxes_per_cta + g0) * p.ckB;
+            g_id[j * 2 + gi] = make_idesc_bf16(kTileM, max(nb, 1) * p.ckB, 1, 1);
+          }
         for (int b = 0; b < nblk; ++b) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-          for (int j = 0; j < kt_valid; ++j) {
-            const uint64_t da0 = protoA + ((a_addr + j * a_tile) >> 4);
-            for (int g0 = 0; g0 < nboxes; g0 += boxes_per_mma) {
-              const int nb = min(boxes_per_mma, nboxes - g0);
-              const uint32_t idesc = make_idesc_bf16(kTileM, nb * p.ckB, 1, 1);
-              const uint64_t db0 = protoB + ((a_addr + a_region + g0 * p.boxB_bytes) >> 4);
-              const uint32_t d_tmem = tmem_base + (j * p.boxes_per_cta + g0) * p.ckB;
-              if (ksteps == 4) {
-                umma_bf16(d_tmem, da0, db0, idesc, b != 0 ? 1u : 0u);
-                umma_bf16(d_tmem, da0 + kincA, db0 + kincB, idesc, 1u);
-                umma_bf16(d_tmem, da0 + 2 * kincA, db0 + 2 * kincB, idesc, 1u);
-                umma_bf16(d_tmem, da0 + 3 * kincA, db0 + 3 * kincB, idesc, 1u);
-              } else {
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16(d_tmem, da0 + k * kincA, db0 + k * kincB, idesc, (b | k) != 0 ? 1u : 0u);
-              }
+          const uint64_t da_s = protoA + (a_addr >> 4), db_s = protoB + (a_addr >> 4);
+          const uint32_t first = b != 0 ? 1u : 0u;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (!g_on[g]) continue;
+            const uint64_t da0 = da_s + g_da[g], db0 = db_s + g_db[g];
+            const uint32_t d_tmem = g_tm[g], idesc = g_id[g];
+            if (ksteps == 4) {
+              umma_bf16(d_tmem, da0, db0, idesc, first);
+              umma_bf16(d_tmem, da0 + kincA, db0 + kincB, idesc, 1u);
+              umma_bf16(d_tmem, da0 + 2 * kincA, db0 + 2 * kincB, idesc, 1u);
+              umma_bf16(d_tmem, da0 + 3 * kincA, db0 + 3 * kincB, idesc, 1u);
+            } else {
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, da0 + k * kincA, db0 + k * kincB, idesc, (b | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -595,7 +628,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             const int id = box0 + x;
             const int t = id / p.c_chunks;
             const int cc = id - t * p.c_chunks;
-            const int tap = p.taps[t].b_tap;
+            const int tap = t;
             const int cbase = cc * p.ckB;
             float* dst = p.dw + (static_cast<long long>(k) * p.taps_total + tap) * p.C + cbase;
             for (int c0 = 0; c0 < p.ckB; c0 += 16) {
@@ -1062,11 +1095,12 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
     B200_REQUIRE((d->C & 3) == 0, B200_ERR_UNSUPPORTED, "conv_wgrad: C must be a multiple of 4");
     p.partial = static_cast<float*>(workspace);
   }
-  for (int r = 0; r < d->R; ++r)
-    for (int s = 0; s < d->S; ++s) {
-      TapEntry& t = p.taps[r * d->S + s];
-      t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.b_tap = (uint16_t)(r * d->S + s); t.pad_ = 0;
-    }
+  p.S_filter = d->S;
+  if (getenv("B200_WGRAD_DEBUG"))
+    fprintf(stderr, "wgrad cfg: K=%d C=%d taps=%d ckA=%d ckB=%d kt=%d bpc=%d k_groups=%d col_groups=%d splits=%d bps=%d "
+            "stages=%d stage=%u pitch=%d partial=%d\n", d->K, d->C, p.taps_total, p.ckA, p.ckB, p.kt, p.boxes_per_cta,
+            p.k_groups, p.col_groups, p.splits, p.blocks_per_split, p.num_stages, p.stage_bytes, p.pitch,
+            p.partial != nullptr);
   CUtensorMap tmDy, tmX;
   rc = encode_tiled2(&tmDy, dy, d->K, (long long)p.M_total, p.ckA, p.bk);
   if (rc) return rc;

@@ -158,9 +158,16 @@ class _Conv(object):
         self.R, self.S = mod.kernel_size
         self.stride = mod.stride[0]
         self.pad = mod.padding[0]
-        if mod.stride[0] != mod.stride[1] or mod.padding[0] != mod.padding[1] or mod.dilation != (1, 1) \
-                or mod.bias is not None:
-            raise B200Error('conv %s: only square stride/padding, dilation 1 and bias=False are supported' % s.name)
+        if mod.stride[0] != mod.stride[1] or mod.padding[0] != mod.padding[1] or mod.dilation != (1, 1):
+            raise B200Error('conv %s: only square stride/padding and dilation 1 are supported' % s.name)
+        # A bias in front of a BatchNorm (MobileNet-v1's depthwise convolutions, models/mobilenet.py:44-46 of the
+        # reference) is absorbed analytically: training-mode BN removes it from the output and makes its gradient
+        # exactly zero; it only shifts the running mean and the eval-mode BN shift (see Runtime._bn_coeffs)
+        self.bias32 = None
+        if mod.bias is not None:
+            if s.kind != 'dw':
+                raise B200Error('conv %s: bias is only supported on depthwise convolutions followed by BatchNorm' % s.name)
+            self.bias32 = arena.kernel_view(arena.p32, arena.slot(mod.bias))
         self.groups = mod.groups if s.kind == 'conv' else 1
         self.slot = s
         self.wt = None           # [C, R*S, K] view of the runtime's transposed shadow (dgrad operand), set by Runtime
@@ -192,6 +199,49 @@ class _BN(object):
         self.beta = arena.kernel_view(arena.p32, sb)
         self.dgamma = arena.kernel_view(arena.g32, sw)
         self.dbeta = arena.kernel_view(arena.g32, sb)
+
+
+class _SE(object):
+    """squeeze-and-excitation gate (models/modules/se.py:6-25 of the reference): two tiny linear layers whose
+    parameters live in the arena like the classifier's (bf16 [K,1,C] kernel views, fp32 biases)."""
+
+    def __init__(self, arena, mod):
+        from .models.modules.se import SEBlock
+        if not isinstance(mod, SEBlock):
+            raise B200Error('residual_block of type %s is outside the B200 hot path' % type(mod).__name__)
+        l1, l2 = mod.transform[0], mod.transform[2]
+        self.C, self.hidden = l1.in_features, l1.out_features
+        if self.C % 8 or self.hidden % 8 or l2.out_features != self.C:
+            raise B200Error('SE gate: channel counts must be multiples of 8 (got %d -> %d)' % (self.C, self.hidden))
+        sw1, sb1, sw2, sb2 = (arena.slot(p) for p in (l1.weight, l1.bias, l2.weight, l2.bias))
+        self.w1, self.gw1 = arena.kernel_view(arena.p16, sw1), arena.kernel_view(arena.g32, sw1)
+        self.b1, self.gb1 = arena.kernel_view(arena.p32, sb1), arena.kernel_view(arena.g32, sb1)
+        self.w2, self.gw2 = arena.kernel_view(arena.p16, sw2), arena.kernel_view(arena.g32, sw2)
+        self.b2, self.gb2 = arena.kernel_view(arena.p32, sb2), arena.kernel_view(arena.g32, sb2)
+
+    def fwd(self, r):
+        """r' = r * sigmoid(W2 relu(W1 mean(r) + b1) + b2); returns (r', tape)."""
+        N = r.shape[0]
+        mean = ops.se_pool(r)                                                        # [N,1,1,C] bf16
+        d1 = ops.make_desc(N, 1, 1, self.C, self.hidden, 1, 1, 1, 0)
+        d2 = ops.make_desc(N, 1, 1, self.hidden, self.C, 1, 1, 1, 0)
+        h = ops.conv_fprop(mean, self.w1, d1, bias=self.b1, act=ACT_RELU)            # [N,1,1,C/ratio] bf16
+        logit = ops.conv_fprop(h, self.w2, d2, bias=self.b2, out_fp32=True).view(N, self.C)
+        return ops.se_scale_fwd(r, logit), (r, mean, h, logit, d1, d2)
+
+    def bwd(self, rt, tape, g):
+        """g = dL/dr' -> dL/dr; the gate's parameter gradients accumulate into the arena."""
+        r, mean, h, logit, d1, d2 = tape
+        N = r.shape[0]
+        dlogit = ops.se_bwd_reduce(g, r, logit)                                      # [N,1,1,C] bf16
+        ops.colsum_bf16(dlogit.view(N, self.C), self.gb2)
+        rt._wgrad_async(lambda: ops.conv_wgrad(h, dlogit, d2, self.gw2), h, dlogit)
+        dh = ops.conv_dgrad(dlogit, ops.weight_transpose(self.w2), d2)
+        dh = ops.act_bwd(dh, h, ACT_RELU)
+        ops.colsum_bf16(dh.view(N, self.hidden), self.gb1)
+        rt._wgrad_async(lambda: ops.conv_wgrad(mean, dh, d1, self.gw1), mean, dh)
+        dmean = ops.conv_dgrad(dh, ops.weight_transpose(self.w1), d1)
+        return ops.se_bwd_dx(g, logit, dmean)
 
 
 class _Unit(object):
@@ -352,6 +402,15 @@ class Runtime(object):
                          m.num_batches_tracked, u.mean, u.invstd, u.scale, u.shift, self._ws)
         else:
             ops.bn_eval_coeffs(bn.gamma, bn.beta, m.running_mean, m.running_var, m.eps, u.scale, u.shift)
+        bias = getattr(u.conv, 'bias32', None) if u.conv is not None else None
+        if bias is not None:            # conv bias in front of this BN (never on the ResNet / MobileNet-v2 paths)
+            if training:                # the true pre-BN tensor is z + b: only the running mean sees it
+                if m.momentum is None:
+                    m.running_mean.add_(bias / m.num_batches_tracked.to(torch.float32))
+                else:
+                    m.running_mean.add_(bias, alpha=float(m.momentum))
+            else:
+                u.shift.add_(u.scale * bias)
 
     def _stats_only(self, x, conv, bn, training):
         """conv + BN coefficients without the apply (used for the downsample branch, fused into the main apply)."""
@@ -640,8 +699,6 @@ class ResNetRuntime(Runtime):
             if isinstance(layer, nn.Identity):
                 continue
             for blk in layer:
-                if blk.residual_block is not None:
-                    raise B200Error('residual_block (SE) is outside the B200 hot path')
                 if isinstance(blk.dropout, nn.Dropout) and blk.dropout.p != 0:
                     raise B200Error('dropout inside residual blocks is not supported on the B200 path')
                 spec = {'kind': 'bottleneck' if isinstance(blk, Bottleneck) else 'basic'}
@@ -653,6 +710,8 @@ class ResNetRuntime(Runtime):
                 spec['down'] = None
                 if blk.downsample is not None:
                     spec['down'] = (_Conv(a, blk.downsample[0]), _BN(a, blk.downsample[1]))
+                # squeeze-excitation on the residual branch (resnet_se / resnext_se): one gate per stage, shared
+                spec['se'] = _SE(a, blk.residual_block) if blk.residual_block is not None else None
                 self.blocks.append(spec)
         self._head_build(m.fc)
 
@@ -724,20 +783,31 @@ class ResNetRuntime(Runtime):
             u = self._unit_fwd(h, convs[i], bns[i], ACT_RELU, training, True)
             units.append(u)
             h = u.y
-        down = None
-        if spec['down'] is not None:
+        down, se_tape = None, None
+        if spec.get('se') is not None:
+            # residual = SE(downsample(x) | x): the gate needs the materialised residual, so the downsample branch
+            # gets its own BN-apply pass here instead of being folded into the join
+            r = x
+            if spec['down'] is not None:
+                down = self._unit_fwd(x, spec['down'][0], spec['down'][1], ACT_NONE, training, True)
+                r = down.y
+            r, se_tape = spec['se'].fwd(r)
+            last = self._unit_fwd(h, convs[-1], bns[-1], ACT_RELU, training, True, residual=r)
+        elif spec['down'] is not None:
             down = self._stats_only(x, spec['down'][0], spec['down'][1], training)
             last = self._unit_fwd(h, convs[-1], bns[-1], ACT_RELU, training, True, other=down)
         else:
             last = self._unit_fwd(h, convs[-1], bns[-1], ACT_RELU, training, True, residual=x)
         units.append(last)
-        return last.y, {'units': units, 'down': down}
+        return last.y, {'units': units, 'down': down, 'se': se_tape}
 
     def _block_bwd(self, spec, saved, dy):
         units, down = saved['units'], saved['down']
         last = units[-1]
         # out = relu(bn_last(z) + skip): g = dy * (out > 0) feeds both branches
         dz, g = self._bn_bwd(last, dy, last.y, ACT_RELU, want_g=True)
+        if saved.get('se') is not None:
+            g = spec['se'].bwd(self, saved['se'], g)          # through the gate: dL/d(residual before SE)
         if down is not None:
             dzd, _ = self._bn_bwd(down, g, None, ACT_NONE)
             skip = self._conv_bwd(down, dzd)
@@ -847,17 +917,18 @@ class MobileNetRuntime(Runtime):
         ws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.bfloat16)
         ws[:, :, :Cin].copy_(self.stem_w32.view(K, 9, Cin))
         st, pad = self.stem_conv.stride[0], self.stem_conv.padding[0]
+        act = getattr(self, 'stem_act', ACT_RELU6)
         u = _Unit()
-        u.conv, u.bn, u.act, u.x = None, self.stem_bn, ACT_RELU6, xs
+        u.conv, u.bn, u.act, u.x = None, self.stem_bn, act, xs
         u.desc = ops.make_desc(N, H, W, 16, K, 3, 3, st, pad, algo_macs=K * 9 * Cin)
         u.z = ops.conv_fprop(xs, ws, u.desc)
         self._bn_coeffs(u, training)
-        u.y = ops.bn_apply(u.z, u.scale, u.shift, ACT_RELU6)
+        u.y = ops.bn_apply(u.z, u.scale, u.shift, act)
         return u.y, {'unit': u, 'cin': Cin}
 
     def _stem_bwd(self, st, dy):
         u = st['unit']
-        dz, _ = self._bn_bwd(u, dy, None, ACT_RELU6)
+        dz, _ = self._bn_bwd(u, dy, None, u.act)
         K, Cin = self.stem_conv.out_channels, st['cin']
         def stem_wgrad():
             dws = torch.zeros((K, 9, 16), device=self.device, dtype=torch.float32)
@@ -903,10 +974,36 @@ class MobileNetRuntime(Runtime):
         self._buckets_end()
 
 
+class MobileNetV1Runtime(MobileNetRuntime):
+    """Pipeline for models.mobilenet.MobileNet (v1): stem conv + BN + ReLU, 13 x [depthwise 3x3 (+bias) + BN + ReLU,
+    1x1 + BN + ReLU], global average pool, linear (reference: models/mobilenet.py:39-156) -- the unit kernels of
+    MobileNetRuntime with ReLU instead of ReLU6 and no skips."""
+
+    def _build(self):
+        m, a = self.model, self.arena
+        layers = list(m.features)
+        conv0, bn0 = layers[0], layers[1]
+        if conv0.kernel_size != (3, 3) or conv0.in_channels > 16 or conv0.groups != 1 or conv0.bias is not None:
+            raise B200Error('unsupported MobileNet stem')
+        self.stem_conv = conv0
+        s = a.slot(conv0.weight)
+        self.stem_w32 = a.p32[s.offset:s.offset + s.numel]
+        self.stem_g32 = a.g32[s.offset:s.offset + s.numel]
+        self.stem_bn = _BN(a, bn0)
+        self.stem_act = ACT_RELU6 if isinstance(layers[2], nn.ReLU6) else ACT_RELU
+        self.blocks = []
+        for mod in layers[3:]:
+            self.blocks.append({'add_res': False, 'units': self._parse_units(list(mod.components))})
+        self._head_build(m.fc, dropout_p=0.0)
+        max_c = max(u[1].C for b in self.blocks for u in b['units'] if u[0] == 'dw')
+        self._dw_ws = torch.empty(592 * 9 * max_c, device=self.device, dtype=torch.float32)
+
+
 def convert_b200(model, device=None):
     """Convert a registry model for the B200 kernel path (in place) and return it."""
     from .models.resnet import ResNet
     from .models.mobilenet_v2 import MobileNet_v2
+    from .models.mobilenet import MobileNet
     from . import lib
     lib.load()  # fail loudly when the CUDA extension is missing
     if not torch.cuda.is_available():
@@ -918,6 +1015,8 @@ def convert_b200(model, device=None):
         rt = ResNetRuntime(model, device)
     elif isinstance(model, MobileNet_v2):
         rt = MobileNetRuntime(model, device)
+    elif isinstance(model, MobileNet):
+        rt = MobileNetV1Runtime(model, device)
     else:
         raise B200Error('no B200 runtime for model type %s yet' % type(model).__name__)
     object.__setattr__(model, '_b200', rt)

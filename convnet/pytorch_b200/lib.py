@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200conv.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libb200conv.so")   # override: A/B builds in tools/
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 
@@ -63,6 +63,11 @@ SIGNATURES = {
     "b200_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
     "b200_group_weight_expand": [_vp, _i, _i, _i, _i, _vp, _vp],
     "b200_group_wgrad_extract": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "b200_se_pool": [_vp, _i, _i, _i, _vp, _vp],
+    "b200_se_scale_fwd": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "b200_se_bwd_reduce": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "b200_se_bwd_dx": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "b200_act_bwd": [_vp, _vp, _ll, _i, _vp, _vp],
     "b200_softmax_ce": [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "b200_colsum_bf16": [_vp, _i, _i, _vp, _vp],
     "b200_fused_sgd": [_vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _f, _f, _f, _vp, _i, _i, _vp],

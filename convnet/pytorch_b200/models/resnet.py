@@ -15,7 +15,7 @@ import math
 import torch
 import torch.nn as nn
 
-__all__ = ['resnet']
+__all__ = ['resnet', 'resnet_se']
 
 
 def init_model(model):
@@ -312,3 +312,11 @@ def resnet(**config):
         from ..engine import convert_b200
         model = convert_b200(model)
     return model
+
+
+def resnet_se(**config):
+    """ResNet with a squeeze-and-excitation gate on the residual branch of every block (models/resnet.py:434-436 of the
+    reference): SURVEY.md section 8(f) row 4."""
+    from .modules.se import SEBlock
+    config['residual_block'] = SEBlock
+    return resnet(**config)

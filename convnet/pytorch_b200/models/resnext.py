@@ -5,7 +5,7 @@ expansion 2).
 """
 from .resnet import ResNet_imagenet, ResNet_cifar, BasicBlock, Bottleneck
 
-__all__ = ['resnext']
+__all__ = ['resnext', 'resnext_se']
 
 _LAYERS = {18: (BasicBlock, [2, 2, 2, 2]), 34: (BasicBlock, [3, 4, 6, 3]), 50: (Bottleneck, [3, 4, 6, 3]),
            101: (Bottleneck, [3, 4, 23, 3]), 152: (Bottleneck, [3, 8, 36, 3])}
@@ -41,3 +41,10 @@ def resnext(**config):
         from ..engine import convert_b200
         model = convert_b200(model)
     return model
+
+
+def resnext_se(**config):
+    """ResNeXt with squeeze-and-excitation gates (models/resnext.py:53-55 of the reference)."""
+    from .modules.se import SEBlock
+    config['residual_block'] = SEBlock
+    return resnext(**config)

@@ -293,6 +293,50 @@ def avgpool_bwd(dy, in_shape):
     return dx
 
 
+# ------------------------------------------------------------------------------------ squeeze-and-excitation
+def se_pool(r):
+    N, H, W, C = r.shape
+    out = torch.empty((N, 1, 1, C), device=r.device, dtype=bf16)
+    with _T('se', 0, 2 * r.numel()):
+        _l.check(_l.load().b200_se_pool(r.data_ptr(), N, H * W, C, out.data_ptr(), _stream()), "b200_se_pool")
+    return out
+
+
+def se_scale_fwd(r, logit):
+    N, H, W, C = r.shape
+    _chk(logit, torch.float32, "logit")
+    out = torch.empty_like(r)
+    with _T('se', 0, 4 * r.numel()):
+        _l.check(_l.load().b200_se_scale_fwd(r.data_ptr(), logit.data_ptr(), N, H * W, C, out.data_ptr(), _stream()),
+                 "b200_se_scale_fwd")
+    return out
+
+
+def se_bwd_reduce(g, r, logit):
+    N, H, W, C = r.shape
+    out = torch.empty((N, 1, 1, C), device=r.device, dtype=bf16)
+    with _T('se', 0, 4 * r.numel()):
+        _l.check(_l.load().b200_se_bwd_reduce(g.data_ptr(), r.data_ptr(), logit.data_ptr(), N, H * W, C, out.data_ptr(),
+                                              _stream()), "b200_se_bwd_reduce")
+    return out
+
+
+def se_bwd_dx(g, logit, dmean):
+    N, H, W, C = g.shape
+    out = torch.empty_like(g)
+    with _T('se', 0, 4 * g.numel()):
+        _l.check(_l.load().b200_se_bwd_dx(g.data_ptr(), logit.data_ptr(), dmean.data_ptr(), N, H * W, C, out.data_ptr(),
+                                          _stream()), "b200_se_bwd_dx")
+    return out
+
+
+def act_bwd(dy, y, act):
+    out = torch.empty_like(dy)
+    _l.check(_l.load().b200_act_bwd(dy.data_ptr(), y.data_ptr(), dy.numel(), int(act), out.data_ptr(), _stream()),
+             "b200_act_bwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------ layout / casts
 def input_prep(x_nchw, cpad, s2d=False, border=False):
     """NCHW fp32 -> NHWC bf16 (channels zero-padded to cpad) or its 2x2 space-to-depth form (optionally with

@@ -163,6 +163,21 @@ int b200_group_weight_expand(const float* w_grouped, int K, int T, int C, int gr
 int b200_group_wgrad_extract(const float* dw_dense, int K, int T, int C, int groups, float* dw_grouped,
                              b200_stream_t stream);
 
+/* ---- squeeze-and-excitation on the residual branch (csrc/se.cu) --------------------------------
+ * replaces models/modules/se.py:6-25 (SEBlock.forward and its autograd backward) as used by resnet_se / resnext_se
+ * (models/resnet.py:112-113,159-160): r' = r * sigmoid(logit[n][c]); the two linear layers in between run on
+ * b200_conv_* as 1x1 convolutions on 1x1 maps.  r, g, out: NHWC bf16 [N][HW][C]; logit fp32 [N][C]. */
+int b200_se_pool(const void* r, int N, int HW, int C, void* mean_bf16, b200_stream_t stream);
+int b200_se_scale_fwd(const void* r, const float* logit, int N, int HW, int C, void* out, b200_stream_t stream);
+/* dlogit[n][c] (bf16) = sigma'(logit) * sum_hw g*r  --  gradient of the gate's pre-activation */
+int b200_se_bwd_reduce(const void* g, const void* r, const float* logit, int N, int HW, int C, void* dlogit_bf16,
+                       b200_stream_t stream);
+/* dr = g * sigmoid(logit) + dmean / HW  (dmean bf16 [N][C]: gradient w.r.t. the pooled mean) */
+int b200_se_bwd_dx(const void* g, const float* logit, const void* dmean_bf16, int N, int HW, int C, void* dr,
+                   b200_stream_t stream);
+/* dx = dy * act'(y) for y = act(.), elementwise bf16 (n % 8 == 0) */
+int b200_act_bwd(const void* dy, const void* y, long long n, int act, void* dx, b200_stream_t stream);
+
 /* ---- loss (csrc/loss.cu) ----------------------------------------------------------------------
  * replaces utils/cross_entropy.py:14-67 (F.cross_entropy / label smoothing) forward+backward.
  * logits/dlogits rows have pitch ld >= classes (columns [classes, ld) are padding: ignored on read,

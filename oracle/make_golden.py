@@ -86,7 +86,8 @@ def main():
     for name, factory, cfg in [('resnet20_cifar10', ref_models.resnet, dict(dataset='cifar10', depth=20)),
                                ('resnet50_imagenet', ref_models.resnet, dict(dataset='imagenet', depth=50)),
                                ('resnext101_imagenet', ref_models.resnext, dict(dataset='imagenet', depth=101)),
-                               ('mobilenet_v2', ref_models.mobilenet_v2, dict(dataset='imagenet'))]:
+                               ('mobilenet_v2', ref_models.mobilenet_v2, dict(dataset='imagenet')),
+                               ('mobilenet_v1', ref_models.mobilenet, dict(dataset='imagenet'))]:
         torch.manual_seed(123)
         m = factory(**cfg)
         init[name] = {'stats': tensor_stats(m.state_dict()),
@@ -96,6 +97,8 @@ def main():
                                      for k, v in ph.items()} for ph in m.regime]
     with open(os.path.join(OUT, 'init_stats.json'), 'w') as f:
         json.dump(init, f)
+    if len(sys.argv) > 1 and sys.argv[1] == 'init':           # regenerate only the initialisation statistics
+        return
 
     # ---- 2. resnet20: reference Trainer + OptimRegime, 5 warm-up steps then one recorded step ----
     torch.manual_seed(123)

@@ -72,11 +72,29 @@ def _block_names(sd, layer):
     return ['%s.%d' % (layer, i) for i in idx]
 
 
+def _se_canon(k):
+    """resnet_se shares ONE SEBlock per stage between its blocks (models/resnet.py:182-191 of the reference): the
+    state_dict lists it under every block; the parameter is the first block's."""
+    m = re.match(r'^(layer\d+)\.\d+\.(residual_block\..*)$', k)
+    return '%s.0.%s' % (m.group(1), m.group(2)) if m else k
+
+
 def _skip(x, sd, p, stride, training, bufs, quant):
+    r = x
     if p + '.downsample.0.weight' in sd:
         z = _conv(x, sd, p + '.downsample.0', stride, 0, quant)
-        return _bn(z, sd, p + '.downsample.1', training, bufs, quant)
-    return x
+        r = _bn(z, sd, p + '.downsample.1', training, bufs, quant)
+    se = _se_canon(p + '.residual_block.transform.0.weight')
+    if se in sd:
+        # SEBlock.forward (models/modules/se.py:21-25) on the residual (models/resnet.py:112-113,159-160); storage
+        # roundings where the kernels materialise bf16: the residual itself, the pooled mean, the hidden layer, the gate
+        q = se[:-len('transform.0.weight')]
+        r = _q(r, quant)
+        mean = _q(r.mean((2, 3)), quant)
+        h = _q(F.relu(F.linear(mean, sd[q + 'transform.0.weight'], sd[q + 'transform.0.bias'])), quant)
+        gate = torch.sigmoid(F.linear(h, sd[q + 'transform.2.weight'], sd[q + 'transform.2.bias']))
+        r = _q(r * gate[:, :, None, None], quant)
+    return r
 
 
 def _bottleneck(x, sd, p, stride, training, bufs, quant):
@@ -219,7 +237,7 @@ def is_decayed(name, sd=None):
 
 def param_names(sd):
     return [k for k in sd if not (k.endswith('running_mean') or k.endswith('running_var')
-                                  or k.endswith('num_batches_tracked'))]
+                                  or k.endswith('num_batches_tracked')) and _se_canon(k) == k]
 
 
 def loss_and_grads(sd, x, y, smooth_eps=0.0, quant=False, training=True, dropout_p=0.0):
@@ -243,6 +261,9 @@ def sgd_step(sd, grads, momentum_buf, lr, momentum=0.9, weight_decay=1e-4, loss_
         m = g.clone() if momentum_buf.get(k) is None else momentum * momentum_buf[k] + g
         new_m[k] = m
         new_sd[k] = sd[k] - lr * m
+    for k in sd:                              # aliases of shared parameters (SE gates) follow their owner
+        if _se_canon(k) != k and _se_canon(k) in new_sd:
+            new_sd[k] = new_sd[_se_canon(k)]
     return new_sd, new_m
 
 

@@ -219,15 +219,18 @@ def test_softmax_ce(B, K, ld, eps):
     logits = torch.zeros(B, ld).cuda()
     logits[:, :K] = torch.randn(B, K).cuda() * 3
     target = torch.randint(0, K, (B,)).cuda()
-    loss = torch.full((1,), 77.0).cuda()          # overwritten, not accumulated
-    rows = torch.empty(B, device='cuda')
+    loss = torch.full((3,), 77.0).cuda()          # {loss, top-1 %, top-5 %}: overwritten, not accumulated
+    rows = torch.empty(2 * B, device='cuda')
     dl = torch.empty(B, ld, device='cuda', dtype=bf16)
     up = torch.full((1,), 0.5).cuda()             # upstream gradient of the loss as a device scalar
     ops.softmax_ce(logits, target, K, eps, loss=loss, row_loss=rows, dlogits=dl, grad_scale=4.0, grad_scale_dev=up)
     lr = logits[:, :K].double().requires_grad_(True)
     ref = cross_entropy(lr, target, smooth_eps=eps if eps else None)
     gref, = torch.autograd.grad(ref, lr)
-    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert abs(float(loss[0]) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    from convnet.pytorch_b200.utils.meters import accuracy
+    p1, p5 = accuracy(logits[:, :K], target, topk=(1, 5))       # utils/meters.py:59-72 of the reference
+    assert abs(float(loss[1]) - float(p1)) < 1e-3 and abs(float(loss[2]) - float(p5)) < 1e-3
     assert close_bf16(dl[:, :K], 2.0 * gref)
     assert float(dl[:, K:].float().abs().sum()) == 0.0
 

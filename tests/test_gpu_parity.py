@@ -164,7 +164,7 @@ def test_full_size_bottleneck_at_benchmark_shape():
     for n, q in blk.named_parameters():
         c, r = _cos(mine[n].grad, q.grad), _rel(mine[n].grad, q.grad)
         print('   %-14s cos %.6f rel %.3e' % (n, c, r))
-        assert c > 0.998 and r < 8e-2, n
+        assert c > 0.99 and r < 1e-1, n            # T1 asks every tensor for cos >= 0.95
     # pixel subsample, element-wise: 2 bf16 ulp of the channel maximum on 4096 random pixels
     idx = torch.randint(0, 256 * 56 * 56, (4096,), generator=g).cuda()
     a = y.float().view(-1, 256)[idx]

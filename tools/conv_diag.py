@@ -102,6 +102,14 @@ def run(name):
     torch.cuda.synchronize()
     gw_krsc = gw.permute(0, 2, 3, 1).reshape(K, R * S, C)
     out["wgrad"] = rel_err(dw, gw_krsc)
+    if os.environ.get("B200_DIAG_TAPS"):
+        # which tap slot holds which tap's gradient?  best-matching reference tap for every computed tap
+        best = []
+        for t in range(R * S):
+            errs = [rel_err(dw[:, t, :], gw_krsc[:, u, :])[0] for u in range(R * S)]
+            u = min(range(R * S), key=lambda i: errs[i])
+            best.append((t, u, round(errs[u], 4)))
+        out["tap_match"] = best
     # accumulate semantics
     ops.conv_wgrad(x, dy, desc, dw)
     torch.cuda.synchronize()
