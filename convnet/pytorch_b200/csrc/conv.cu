@@ -49,6 +49,8 @@ struct IgemmParams {
   int tma_store;         // 1: dense bf16 output staged in smem and written by TMA (tmC), residual via tmR
   int plain_a;           // 1: A is a dense [M_total, SC] matrix (1x1, stride 1, no padding): tiled TMA
   int b_stationary;      // 1: every (tap, k-block) weight slice stays in shared memory (small 1x1 layers): only A streams
+  int window;            // > 0: block-diagonal convolution -- n-tile b (block_n == window) reads source channels
+                         // [window*b, window*b + window) only; the weight operand is [N_total][taps][window]
   double* stats;         // fused BN statistics accumulators [kStatReplicas][2][N_total] (BN workspace) or nullptr
   void* out;
   const void* res;
@@ -202,10 +204,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + p.a_bytes;
             mbar_arrive_expect_tx(&full_bar[stage], p.b_stationary ? p.a_bytes : p.tx_bytes);
+            const int a_c = cc * p.ck + (p.window ? n_tile * p.window : 0);
             if (p.plain_a)  // 1x1 / stride 1: the A operand is a dense [M, C] matrix -> tiled TMA (faster than im2col)
-              tma_load_2d(&tmA, &full_bar[stage], sa, cc * p.ck, m0);
+              tma_load_2d(&tmA, &full_bar[stage], sa, a_c, m0);
             else
-              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cc * p.ck, base_w, base_h, img, te.off_w, te.off_h);
+              tma_load_im2col_4d(&tmA, &full_bar[stage], sa, a_c, base_w, base_h, img, te.off_w, te.off_h);
             if (!p.b_stationary) tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.ck, te.b_tap, n_tile * p.block_n);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
           }
@@ -429,6 +432,7 @@ struct WgradParams {
   int plain_x;           // 1: x is a dense [M_total, C] matrix (1x1 stride 1): tiled TMA instead of im2col
   float* partial;        // split-K partial tiles [tile][split][128][pitch] (nullptr: splits == 1, add into dw)
   int pitch;             // kt * boxes_per_cta * ckB
+  int window;            // 0 dense; 128: k-tile t pairs with source channels [128t, 128t+128) only (kt == 1)
   int S_filter;          // filter width: tap t = (r, s) = (t / S, t % S) gives the im2col offsets {s, r}.  Computed, not
                          // read from a table: ptxas 12.9 (sm_100a) mis-split a 32-bit {off_w, off_h} word loaded through
                          // the uniform datapath (LDCU + UPRMT on a stale register) -- wrong off_h for every tap row > 0
@@ -508,7 +512,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           const int id = box0 + min(x, nboxes - 1);
           const int t = id / p.c_chunks;
           const int th = t / p.S_filter;
-          box_c[x] = (id - t * p.c_chunks) * p.ckB;
+          box_c[x] = (id - t * p.c_chunks) * p.ckB + (p.window ? k0 : 0);
           box_w[x] = static_cast<uint16_t>(t - th * p.S_filter);
           box_h[x] = static_cast<uint16_t>(th);
         }
@@ -797,6 +801,7 @@ struct IgemmLaunch {
   void* out; int OH, OW, os, oh0, ow0, ldo;
   const void* res; const float* bias; int act, out_fp32;
   double* stats;
+  int window;
 };
 
 static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
@@ -813,6 +818,15 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.m_tiles = (p.M_total + kTileM - 1) / kTileM;
   p.ck = pick_ck(L.SC);
   p.c_chunks = (L.SC + p.ck - 1) / p.ck;
+  p.window = L.window;
+  if (L.window) {   // block-diagonal: one n-tile per window, its K loop covers the window's channels only
+    B200_REQUIRE(L.window % 64 == 0 && L.window <= 256 && L.SC == L.Nout && L.Nout % L.window == 0, B200_ERR_UNSUPPORTED,
+                 "igemm: window %d needs C == K (C=%d K=%d), K %% window == 0", L.window, L.SC, L.Nout);
+    p.n_tiles = L.Nout / L.window;
+    p.block_n = L.window;
+    p.ck = 64;
+    p.c_chunks = L.window / 64;
+  }
   p.ntaps = L.ntaps;
   p.a_bytes = kTileM * p.ck * 2;
   p.b_bytes = p.block_n * p.ck * 2;
@@ -828,7 +842,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   static const bool bstat_enabled = !(getenv("B200_IGEMM_BSTAT") && atoi(getenv("B200_IGEMM_BSTAT")) == 0);
   const int b_all = L.ntaps * p.c_chunks * (int)p.b_bytes;
   int bstat_bytes = 0;
-  if (bstat_enabled && p.n_tiles == 1 && (p.a_bytes % 1024) == 0 && (p.b_bytes % 1024) == 0 && b_all <= 64 * 1024) {
+  if (bstat_enabled && p.n_tiles == 1 && !L.window && (p.a_bytes % 1024) == 0 && (p.b_bytes % 1024) == 0 && b_all <= 64 * 1024) {
     p.b_stationary = 1;
     bstat_bytes = b_all;
     stage = p.a_bytes;
@@ -858,7 +872,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     rc = encode_im2col(&tmA, L.src, L.Nimg, L.SH, L.SW, L.SC, p.ck, kTileM, L.lower_w, L.lower_h, upper_w, upper_h,
                        L.trav, L.s_pix, L.s_row, L.s_img);
   if (rc) return rc;
-  rc = encode_tiled3(&tmB, L.wmat, L.SC, L.wtaps, L.Nout, p.ck, 1, p.block_n);
+  rc = encode_tiled3(&tmB, L.wmat, L.window ? L.window : L.SC, L.wtaps, L.Nout, p.ck, 1, p.block_n);
   if (rc) return rc;
 
   CUtensorMap tmC, tmR;
@@ -894,6 +908,8 @@ static int check_desc(const b200_conv_desc* d) {
                    (d->x_pixel_stride > 0 && d->x_pixel_stride % 8 == 0 && d->x_row_stride % 8 == 0 &&
                     d->x_image_stride % 8 == 0 && d->x_row_stride > 0 && d->x_image_stride > 0),
                B200_ERR_INVALID, "conv: x strides must all be 0 (dense) or positive multiples of 8 elements");
+  B200_REQUIRE(d->window == 0 || (d->window % 64 == 0 && d->C == d->K && d->C % d->window == 0 && d->x_pixel_stride == 0),
+               B200_ERR_UNSUPPORTED, "conv: window %d needs C == K, C %% window == 0 (C=%d K=%d)", d->window, d->C, d->K);
   return B200_OK;
 }
 
@@ -909,13 +925,14 @@ extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const voi
   B200_REQUIRE(d->C % 8 == 0, B200_ERR_UNSUPPORTED, "conv_fprop: C=%d must be a multiple of 8 (pad the input)", d->C);
   if (d->stride == 1 && d->pad_h == d->pad_w && d->P == d->H + 2 * d->pad_h - d->R + 1 &&
       d->Q == d->W + 2 * d->pad_w - d->S + 1 && d->x_pixel_stride == 0 && (!ep || !ep->out_fp32) &&
-      !(ep && ep->bias && ep->bn_stats_workspace) && halo_eligible(d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h)) {
+      !(ep && ep->bias && ep->bn_stats_workspace) && (d->window == 0 || d->window == 64) &&
+      halo_eligible(d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h)) {
     return launch_halo(x, w, y, ep ? ep->residual : nullptr, ep ? ep->bias : nullptr, d->N, d->P, d->Q, d->C, d->K,
                        d->R, d->S, d->pad_h, 0, ep ? ep->act : 0,
                        (ep && ep->bn_stats_workspace) ? reinterpret_cast<double*>(ep->bn_stats_workspace) : nullptr,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, d->window);
   }
-  if (d->R == 1 && d->S == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && d->x_pixel_stride == 0 &&
+  if (d->R == 1 && d->S == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0 && d->x_pixel_stride == 0 && !d->window &&
       (!ep || !ep->out_fp32) && !(ep && ep->bias && ep->bn_stats_workspace) &&
       pair_eligible((long long)d->N * d->H * d->W, d->C, d->K)) {   // opt-in CTA-pair kernel (conv_pair.cu)
     return launch_pair(x, w, y, ep ? ep->residual : nullptr, ep ? ep->bias : nullptr, (long long)d->N * d->H * d->W, d->C,
@@ -941,6 +958,7 @@ extern "C" int b200_conv_fprop(const b200_conv_desc* d, const void* x, const voi
   L.act = ep ? ep->act : 0;
   L.out_fp32 = ep ? ep->out_fp32 : 0;
   L.stats = (ep && ep->bn_stats_workspace) ? reinterpret_cast<double*>(ep->bn_stats_workspace) : nullptr;
+  L.window = d->window;
   return launch_igemm(L, (cudaStream_t)stream);
 }
 
@@ -954,10 +972,11 @@ extern "C" int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const vo
   const int st = d->stride;
   B200_REQUIRE(st == 1 || st == 2, B200_ERR_UNSUPPORTED, "conv_dgrad: stride %d unsupported", st);
   if (d->R == 3 && d->S == 3 && st == 1 && d->pad_h == 1 && d->pad_w == 1 && d->P == d->H && d->Q == d->W &&
-      halo_eligible(d->H, d->W, d->K, d->C, 3, 3, 1)) {
-    return launch_halo(dy, wt, dx, residual, nullptr, d->N, d->H, d->W, d->K, d->C, 3, 3, 1, 1, 0, nullptr, stream);
+      (d->window == 0 || d->window == 64) && halo_eligible(d->H, d->W, d->K, d->C, 3, 3, 1)) {
+    return launch_halo(dy, wt, dx, residual, nullptr, d->N, d->H, d->W, d->K, d->C, 3, 3, 1, 1, 0, nullptr, stream,
+                       d->window);
   }
-  if (d->R == 1 && d->S == 1 && st == 1 && d->pad_h == 0 && d->pad_w == 0 &&
+  if (d->R == 1 && d->S == 1 && st == 1 && d->pad_h == 0 && d->pad_w == 0 && !d->window &&
       pair_eligible((long long)d->N * d->H * d->W, d->K, d->C)) {   // opt-in CTA-pair kernel: dx = dy * wt^T
     return launch_pair(dy, wt, dx, residual, nullptr, (long long)d->N * d->H * d->W, d->K, d->C, 0, nullptr, stream);
   }
@@ -1013,6 +1032,7 @@ extern "C" int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const vo
       L.I = I; L.J = J; L.trav = 1; L.lower_w = lo_w; L.lower_h = lo_h;
       L.out = dx; L.OH = d->H; L.OW = d->W; L.os = st; L.oh0 = ph; L.ow0 = pw; L.ldo = d->C;
       L.res = residual; L.bias = nullptr; L.act = 0; L.out_fp32 = 0;
+      L.window = d->window;
       rc = launch_igemm(L, stream);
       if (rc) return rc;
     }
@@ -1034,22 +1054,27 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
                "conv_wgrad: C=%d and K=%d must be multiples of 8", d->C, d->K);
   if (d->stride == 1 && d->pad_h == d->pad_w && d->P == d->H + 2 * d->pad_h - d->R + 1 &&
       d->Q == d->W + 2 * d->pad_w - d->S + 1 && d->x_pixel_stride == 0 &&
-      halo_wgrad_eligible(d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h)) {
+      (d->window == 0 || d->window == 128) && halo_wgrad_eligible(d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h)) {
     // partial tiles of the halo kernel must fit the split-K workspace (units * splits <= SMs, or one split)
-    const int units = (d->C / (d->C == 16 ? 16 : 32)) * ((d->K + kTileM - 1) / kTileM);
+    const int cw = d->C == 16 ? 16 : 32;
+    const int units = ((d->window ? d->window : d->C) / cw) * ((d->K + kTileM - 1) / kTileM);
     if (units <= sm_count() + 8)
       return launch_halo_wgrad(x, dy, dw, workspace, workspace_bytes, d->N, d->P, d->Q, d->C, d->K, d->R, d->S, d->pad_h,
-                               stream);
+                               stream, d->window);
   }
+  B200_REQUIRE(d->window == 0 || d->window == 128, B200_ERR_UNSUPPORTED, "conv_wgrad: window must be 0 or 128");
+  // window mode (block-diagonal): k-tile t pairs with input channels [128t, 128t+128) only; dw is [K][taps][128]
+  const int Cw = d->window ? d->window : d->C;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.M_total = d->N * d->P * d->Q;
   p.P = d->P; p.Q = d->Q; p.trav = d->stride; p.lower_w = -d->pad_w; p.lower_h = -d->pad_h;
-  p.K_out = d->K; p.C = d->C; p.taps_total = d->R * d->S;
+  p.K_out = d->K; p.C = Cw; p.taps_total = d->R * d->S;
+  p.window = d->window;
   p.ckA = pick_ck(d->K);
-  p.ckB = pick_ck(d->C);
+  p.ckB = pick_ck(Cw);
   p.bk = 64;  // pixels per TMA box: fewer, larger TMA requests per byte (32-pixel boxes were request-rate bound)
-  p.c_chunks = (d->C + p.ckB - 1) / p.ckB;
+  p.c_chunks = (Cw + p.ckB - 1) / p.ckB;
   p.total_boxes = p.taps_total * p.c_chunks;
   p.k_tiles = (d->K + kTileM - 1) / kTileM;
   p.boxA_bytes = p.bk * p.ckA * 2;
@@ -1060,7 +1085,7 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   static const int kt_cap = getenv("B200_WGRAD_KT") ? atoi(getenv("B200_WGRAD_KT")) : 4;
   double best = 1e30;
   p.kt = 1; p.boxes_per_cta = 1;
-  for (int kt = 1; kt <= 4 && kt <= p.k_tiles && kt <= kt_cap; kt *= 2) {
+  for (int kt = 1; kt <= 4 && kt <= p.k_tiles && kt <= (d->window ? 1 : kt_cap); kt *= 2) {
     int bpc = 512 / (kt * p.ckB);
     if (bpc > 8) bpc = 8;
     if (bpc > p.total_boxes) bpc = p.total_boxes;
@@ -1092,7 +1117,7 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
     B200_REQUIRE(workspace != nullptr && workspace_bytes >= need, B200_ERR_INVALID,
                  "conv_wgrad: workspace too small (%zu < %zu); see b200_conv_wgrad_workspace_bytes()", workspace_bytes,
                  need);
-    B200_REQUIRE((d->C & 3) == 0, B200_ERR_UNSUPPORTED, "conv_wgrad: C must be a multiple of 4");
+    B200_REQUIRE((Cw & 3) == 0, B200_ERR_UNSUPPORTED, "conv_wgrad: C must be a multiple of 4");
     p.partial = static_cast<float*>(workspace);
   }
   p.S_filter = d->S;
@@ -1121,10 +1146,10 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   conv_wgrad_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmDy, tmX, p);
   B200_CHECK_LAUNCH("conv_wgrad_kernel");
   if (p.partial != nullptr) {
-    const long long total = static_cast<long long>(d->K) * p.taps_total * (d->C / 4);
+    const long long total = static_cast<long long>(d->K) * p.taps_total * (Cw / 4);
     long long blocks = (total + 31) / 32;
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
-    conv_wgrad_reduce_kernel<<<static_cast<int>(blocks), 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, d->K, p.taps_total, d->C, p.ckB,
+    conv_wgrad_reduce_kernel<<<static_cast<int>(blocks), 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, d->K, p.taps_total, Cw, p.ckB,
                                                                           p.c_chunks, p.boxes_per_cta, p.kt, p.k_groups,
                                                                           p.splits, p.pitch);
     B200_CHECK_LAUNCH("conv_wgrad_reduce_kernel");

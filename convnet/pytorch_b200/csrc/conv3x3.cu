@@ -40,6 +40,9 @@ struct HaloParams {
   int ntaps, pad;
   int row_bytes;           // bytes of one source pixel chunk: 128 (64 channels) or 32 (16 channels)
   int b_stationary;        // 1: all c_chunks*ntaps weight slices of the n-tile stay in shared memory
+  int diag;                // 1: block-diagonal ("window") convolution: n-tile b (64 outputs) reads input channels
+                           //    [64b, 64b+64) only; a CTA keeps ONE n-tile (its 9 weight slices stay resident) and walks
+                           //    the pixel tiles -- how grouped convolutions run (include/b200conv.h, desc.window)
   uint16_t a_off[kHMaxTaps];  // pixel-row offset of each tap's view inside the halo buffer
   uint16_t b_tap[kHMaxTaps];  // weight tap slice used with it
 };
@@ -80,27 +83,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // tile walk: dense -- tiles (m, n) round-robin over the CTAs; diagonal -- the CTA owns n-tile blockIdx.x % n_tiles and
+  // walks the m-tiles with stride gridDim.x / n_tiles (the grid is a multiple of n_tiles)
+  const int t_start = p.diag ? static_cast<int>(blockIdx.x) / p.n_tiles : static_cast<int>(blockIdx.x);
+  const int t_step = p.diag ? static_cast<int>(gridDim.x) / p.n_tiles : static_cast<int>(gridDim.x);
+  const int total_tiles = p.diag ? p.m_tiles : p.m_tiles * p.n_tiles;
+  const int own_n = static_cast<int>(blockIdx.x) % p.n_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
       int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
       const int cw = p.row_bytes >> 1;   // channels per chunk
-      if (p.b_stationary && blockIdx.x < total_tiles) {
-        // stationary weights: valid because n_tiles == 1 (every tile of this CTA uses the same slices)
+      if (p.b_stationary && t_start < total_tiles) {
+        // stationary weights: every tile of this CTA uses the same slices (n_tiles == 1, or the CTA's own n-tile)
         mbar_arrive_expect_tx(&bstat_bar, static_cast<uint32_t>(p.c_chunks * NTAPS) * p.b_bytes);
         for (int cc = 0; cc < p.c_chunks; ++cc)
           for (int t = 0; t < NTAPS; ++t)
-            tma_load_3d(&tmB, &bstat_bar, sB + (cc * NTAPS + t) * p.b_bytes, cc * cw, p.b_tap[t], 0);
+            tma_load_3d(&tmB, &bstat_bar, sB + (cc * NTAPS + t) * p.b_bytes, cc * cw, p.b_tap[t],
+                        p.diag ? own_n * p.block_n : 0);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      for (int tile = t_start; tile < total_tiles; tile += t_step) {
+        const int m_tile = p.diag ? tile : tile / p.n_tiles, n_tile = p.diag ? own_n : tile - m_tile * p.n_tiles;
         const int img = m_tile / p.tiles_per_img;
         const int h0 = (m_tile - img * p.tiles_per_img) * p.RT;
         for (int cc = 0; cc < p.c_chunks; ++cc) {
           mbar_wait(&a_empty[ia], pa ^ 1u);
           mbar_arrive_expect_tx(&a_full[ia], p.a_box_bytes);
-          tma_load_4d(&tmX, &a_full[ia], sA + ia * p.a_bytes, cc * cw, -p.pad, h0 - p.pad, img);
+          tma_load_4d(&tmX, &a_full[ia], sA + ia * p.a_bytes, (p.diag ? n_tile : cc) * cw, -p.pad, h0 - p.pad, img);
           if (++ia == p.sa) { ia = 0; pa ^= 1u; }
           if (p.b_stationary) continue;
           for (int t = 0; t < NTAPS; ++t) {
@@ -120,12 +129,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       uint32_t tap_inc[NTAPS];
 #pragma unroll
       for (int t = 0; t < NTAPS; ++t) tap_inc[t] = (static_cast<uint32_t>(p.a_off[t]) * p.row_bytes) >> 4;
-      if (p.b_stationary && blockIdx.x < total_tiles) {
+      if (p.b_stationary && t_start < total_tiles) {
         mbar_wait(&bstat_bar, 0);
         tc_fence_after();
       }
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int tile = t_start; tile < total_tiles; tile += t_step, ++local) {
         const int acc = local & 1;
         mbar_wait(&tmem_empty[acc], ((local >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -181,9 +190,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int st_ntile = -1;
     float st_s1 = 0.f, st_s2 = 0.f;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = t_start; tile < total_tiles; tile += t_step, ++local) {
       const int acc = local & 1;
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int m_tile = p.diag ? tile : tile / p.n_tiles, n_tile = p.diag ? own_n : tile - m_tile * p.n_tiles;
       const int img = m_tile / p.tiles_per_img;
       const int h0 = (m_tile - img * p.tiles_per_img) * p.RT;
       const int nbase = n_tile * p.block_n;
@@ -328,9 +337,13 @@ bool halo_eligible(int H, int W, int Cs, int Nout, int R, int S, int pad) {
 
 // dir 0: fprop (tap (r,s) reads halo offset (r,s), weight slice r*S+s); dir 1: dgrad (offset (R-1-r, S-1-s))
 int launch_halo(const void* src, const void* wmat, void* out, const void* res, const float* bias, int N, int H, int W,
-                int Cs, int Nout, int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream) {
+                int Cs, int Nout, int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream, int window) {
   HaloParams p;
   memset(&p, 0, sizeof(p));
+  p.diag = window > 0 ? 1 : 0;
+  if (p.diag)
+    B200_REQUIRE(window == 64 && Cs == Nout && Cs % 64 == 0 && R == 3 && S == 3, B200_ERR_UNSUPPORTED,
+                 "conv halo: window mode needs window == 64, C == K, C %% 64 == 0 and a 3x3 filter (C=%d K=%d)", Cs, Nout);
   p.N = N; p.H = H; p.W = W; p.C = Cs; p.Kout = Nout;
   p.ntaps = R * S; p.pad = pad;
   p.row_bytes = (Cs == 16) ? 32 : 128;
@@ -340,9 +353,9 @@ int launch_halo(const void* src, const void* wmat, void* out, const void* res, c
   if (p.RT > H) p.RT = H;
   p.tiles_per_img = (H + p.RT - 1) / p.RT;
   p.m_tiles = N * p.tiles_per_img;
-  p.n_tiles = (Nout + 255) / 256;
+  p.n_tiles = p.diag ? Nout / 64 : (Nout + 255) / 256;
   p.block_n = Nout / p.n_tiles;
-  p.c_chunks = Cs / cw;
+  p.c_chunks = p.diag ? 1 : Cs / cw;
   p.a_box_bytes = (uint32_t)(p.RT + R - 1) * p.Wp * p.row_bytes;
   uint32_t a_need = (uint32_t)(kHTileM + (R - 1) * p.Wp + (S - 1)) * p.row_bytes;
   if (a_need < p.a_box_bytes) a_need = p.a_box_bytes;
@@ -362,7 +375,8 @@ int launch_halo(const void* src, const void* wmat, void* out, const void* res, c
   const uint32_t epi_bytes = (uint32_t)(p.block_n / 64) * box_pitch;
   int budget = 212 * 1024 - (int)epi_bytes;
   const int b_all = p.c_chunks * p.ntaps * (int)p.b_bytes;
-  p.b_stationary = (p.n_tiles == 1 && b_all <= 80 * 1024) ? 1 : 0;
+  p.b_stationary = ((p.n_tiles == 1 || p.diag) && b_all <= 80 * 1024) ? 1 : 0;
+  B200_REQUIRE(!p.diag || p.b_stationary, B200_ERR_UNSUPPORTED, "conv halo: window mode expects resident weights");
   int b_region;
   if (p.b_stationary) {
     b_region = b_all;
@@ -388,8 +402,9 @@ int launch_halo(const void* src, const void* wmat, void* out, const void* res, c
   if (rc) return rc;
   {
     EncodeTiledFn fn = encode_tiled_fn();
-    cuuint64_t dims[3] = {(cuuint64_t)Cs, (cuuint64_t)p.ntaps, (cuuint64_t)Nout};
-    cuuint64_t strides[2] = {(cuuint64_t)Cs * 2, (cuuint64_t)Cs * p.ntaps * 2};
+    const int wc = p.diag ? window : Cs;      // channel extent of the weight operand: [Nout][taps][wc]
+    cuuint64_t dims[3] = {(cuuint64_t)wc, (cuuint64_t)p.ntaps, (cuuint64_t)Nout};
+    cuuint64_t strides[2] = {(cuuint64_t)wc * 2, (cuuint64_t)wc * p.ntaps * 2};
     cuuint32_t box[3] = {(cuuint32_t)cw, 1, (cuuint32_t)p.block_n};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = fn(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wmat), dims, strides, box, es,
@@ -408,7 +423,13 @@ int launch_halo(const void* src, const void* wmat, void* out, const void* res, c
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   B200_REQUIRE(e == cudaSuccess, B200_ERR_CUDA, "conv halo: smem attribute (%d bytes): %s", smem_bytes, cudaGetErrorString(e));
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
+  int grid = total < sm_count() ? total : sm_count();
+  if (p.diag) {                       // a multiple of n_tiles: every CTA owns one n-tile
+    int per_n = sm_count() / p.n_tiles;
+    if (per_n > p.m_tiles) per_n = p.m_tiles;
+    if (per_n < 1) per_n = 1;
+    grid = per_n * p.n_tiles;
+  }
   if (p.ntaps == 9)
     conv_halo_kernel<9, 4><<<grid, kHThreads, smem_bytes, stream>>>(tmX, tmB, tmC, tmR, p);
   else
@@ -438,6 +459,8 @@ struct HaloWgradParams {
   int x_row_bytes, cw, ncols;
   int c_chunks, k_tiles, units, splits, tiles_per_split;
   int stages;
+  int window;              // 0 dense; 128: block-diagonal -- k-tile t only pairs with input channels [128t, 128t+128):
+                           // units = 4 x k_tiles, dw is [K][taps][128]
   uint32_t a_box_bytes, a_bytes, x_box_bytes, x_bytes;
   float* partial;          // [unit][split][128][ncols]
   uint16_t x_off[kHMaxTaps];
@@ -502,7 +525,7 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_co
           uint8_t* sa = smem + stage * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           for (int j = 0; j < nA; ++j) tma_load_4d(&tmDy, &full_bar[stage], sa + j * 16384, k0 + j * 64, 0, h0, img);
-          tma_load_4d(&tmX, &full_bar[stage], sa + p.a_bytes, cc * p.cw, -p.pad, h0 - p.pad, img);
+          tma_load_4d(&tmX, &full_bar[stage], sa + p.a_bytes, cc * p.cw + (p.window ? k0 : 0), -p.pad, h0 - p.pad, img);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -607,9 +630,13 @@ bool halo_wgrad_eligible(int H, int W, int C, int K_out, int R, int S, int pad) 
 }
 
 int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t workspace_bytes, int N, int H,
-                      int W, int C, int K_out, int R, int S, int pad, cudaStream_t stream) {
+                      int W, int C, int K_out, int R, int S, int pad, cudaStream_t stream, int window) {
   HaloWgradParams p;
   memset(&p, 0, sizeof(p));
+  p.window = window;
+  if (window)
+    B200_REQUIRE(window == 128 && C == K_out && C % 128 == 0, B200_ERR_UNSUPPORTED,
+                 "conv halo wgrad: window mode needs window == 128 and C == K, C %% 128 == 0 (C=%d K=%d)", C, K_out);
   p.N = N; p.H = H; p.W = W; p.K_out = K_out; p.C = C;
   p.ntaps = R * S; p.pad = pad;
   p.cw = (C == 16) ? 16 : 32;
@@ -621,7 +648,7 @@ int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace,
   p.halo_rows = p.RT + R - 1;
   p.tiles_per_img = (H + p.RT - 1) / p.RT;
   p.m_tiles = N * p.tiles_per_img;
-  p.c_chunks = C / p.cw;
+  p.c_chunks = (window ? window : C) / p.cw;       // channel chunks that pair with one k-tile
   p.k_tiles = (K_out + kHTileM - 1) / kHTileM;
   p.units = p.c_chunks * p.k_tiles;
   int splits = sm_count() / p.units;
@@ -663,11 +690,12 @@ int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace,
   else
     conv_halo_wgrad_kernel<4, 4><<<p.units * p.splits, kWThreads, smem_bytes, stream>>>(tmDy, tmX, p);
   B200_CHECK_LAUNCH("conv_halo_wgrad_kernel");
-  const long long total = (long long)K_out * p.ntaps * (C / 4);
+  const int Cw = window ? window : C;                 // row length of dw: [K][taps][Cw]
+  const long long total = (long long)K_out * p.ntaps * (Cw / 4);
   long long blocks64 = (total + 31) / 32;
   if (blocks64 > 16LL * sm_count()) blocks64 = 16LL * sm_count();
   const int blocks = (int)blocks64;
-  conv_halo_wgrad_reduce_kernel<<<blocks, 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, K_out, p.ntaps, C, p.cw, p.k_tiles, p.splits,
+  conv_halo_wgrad_reduce_kernel<<<blocks, 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, K_out, p.ntaps, Cw, p.cw, p.k_tiles, p.splits,
                                                             p.ncols);
   B200_CHECK_LAUNCH("conv_halo_wgrad_reduce_kernel");
   return B200_OK;

@@ -28,11 +28,12 @@ EncodeIm2colFn encode_im2col_fn();
 bool halo_geometry_ok(int H, int W, int Cs, int R, int S, int pad);
 bool halo_eligible(int H, int W, int Cs, int Nout, int R, int S, int pad);
 int launch_halo(const void* src, const void* wmat, void* out, const void* res, const float* bias, int N, int H, int W,
-                int Cs, int Nout, int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream);
+                int Cs, int Nout, int R, int S, int pad, int dir, int act, double* stats, cudaStream_t stream,
+                int window = 0);
 
 bool halo_wgrad_eligible(int H, int W, int C, int K_out, int R, int S, int pad);
 int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t workspace_bytes, int N, int H,
-                      int W, int C, int K_out, int R, int S, int pad, cudaStream_t stream);
+                      int W, int C, int K_out, int R, int S, int pad, cudaStream_t stream, int window = 0);
 
 // conv_pair.cu: EXPERIMENTAL cta_group::2 GEMM for wide 1x1 / stride-1 layers (B200_IGEMM_PAIR=1)
 bool pair_eligible(long long M, int C, int Nout);

@@ -286,28 +286,39 @@ extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, b
   return B200_OK;
 }
 
-// ---- grouped convolution support (ResNeXt): block-diagonal dense expansion of the weights ----------------------
-// w_g fp32 [K][T][C/g]  ->  dense bf16 [K][T][C] with zeros outside the group of output channel k;
-// the dense tcgen05 kernels then serve the grouped layer (extra MACs on zeros, no new data path), and the
-// gradient is extracted from the dense wgrad result.  (reference: nn.Conv2d(groups=32), models/resnext.py:10-16)
+// ---- grouped convolution support (ResNeXt, nn.Conv2d(groups=32), models/resnext.py:10-16) -------------------------
+// A grouped convolution with C == K is block diagonal at ANY granularity that is a multiple of the group width: output
+// channels [W*b, W*b+W) only read input channels of the same window.  The tensor-core kernels run it as K/W independent
+// W-wide diagonal blocks ("window" mode of the conv entry points, W = 64 for fprop/dgrad, 128 for the k-tile of wgrad),
+// so the weight operand is packed per window:
+//   pack      : w_g fp32 [K][T][C/g] -> bf16 [K][T][W],   out[k][t][cl] = w_g[k][t][c - first(k)] if channel
+//               c = W*(k/W) + cl lies in the group of k, else 0                                   (fprop operand)
+//   transposed: bf16 [C][T][W],  out[c][t][kl] = the same weight seen from input channel c, k = W*(c/W) + kl (dgrad operand)
+//   unpack    : dw_g[k][t][cl] += dw_win[k][t][first(k) + cl - W*(k/W)]   from the windowed fp32 gradient [K][T][W]
+// W == C reproduces the dense block-diagonal expansion.
 namespace b200 {
-__global__ void __launch_bounds__(256) group_expand_kernel(const float* __restrict__ wg, int K, int T, int C, int groups,
-                                                           __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256) group_pack_kernel(const float* __restrict__ wg, int K, int T, int C, int groups,
+                                                         int Wd, int transpose, __nv_bfloat16* __restrict__ out) {
   const int cg = C / groups, kg = K / groups;
-  const long long total = (long long)K * T * C;
+  const int rows = transpose ? C : K;
+  const long long total = (long long)rows * T * Wd;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    const int t = (int)((idx / C) % T);
-    const int k = (int)(idx / ((long long)C * T));
-    const int grp = k / kg;
+    const int l = (int)(idx % Wd);
+    const int t = (int)((idx / Wd) % T);
+    const int row = (int)(idx / ((long long)Wd * T));
+    int k, c;
+    if (transpose) { c = row; k = (c / Wd) * Wd + l; } else { k = row; c = (k / Wd) * Wd + l; }
     float v = 0.f;
-    if (c / cg == grp) v = wg[((long long)k * T + t) * cg + (c - grp * cg)];
+    if (k < K && c < C) {
+      const int grp = k / kg;
+      if (c / cg == grp) v = wg[((long long)k * T + t) * cg + (c - grp * cg)];
+    }
     out[idx] = __float2bfloat16(v);
   }
 }
-__global__ void __launch_bounds__(256) group_extract_kernel(const float* __restrict__ dw_dense, int K, int T, int C,
-                                                            int groups, float* __restrict__ dwg) {
+__global__ void __launch_bounds__(256) group_unpack_kernel(const float* __restrict__ dw_win, int K, int T, int C,
+                                                           int groups, int Wd, float* __restrict__ dwg) {
   const int cg = C / groups, kg = K / groups;
   const long long total = (long long)K * T * cg;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -315,29 +326,34 @@ __global__ void __launch_bounds__(256) group_extract_kernel(const float* __restr
     const int cl = (int)(idx % cg);
     const int t = (int)((idx / cg) % T);
     const int k = (int)(idx / ((long long)cg * T));
-    dwg[idx] += dw_dense[((long long)k * T + t) * C + (k / kg) * cg + cl];
+    const int c = (k / kg) * cg + cl;
+    dwg[idx] += dw_win[((long long)k * T + t) * Wd + (c - (k / Wd) * Wd)];
   }
 }
 }  // namespace b200
 
-extern "C" int b200_group_weight_expand(const float* w_grouped, int K, int T, int C, int groups, void* w_dense_bf16,
-                                        b200_stream_t stream) {
-  B200_REQUIRE(w_grouped && w_dense_bf16 && K > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && K % groups == 0,
-               B200_ERR_INVALID, "group_weight_expand: bad argument");
-  const long long total = (long long)K * T * C;
-  b200::group_expand_kernel<<<b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      w_grouped, K, T, C, groups, (__nv_bfloat16*)w_dense_bf16);
-  B200_CHECK_LAUNCH("group_expand_kernel");
+extern "C" int b200_group_weight_pack(const float* w_grouped, int K, int T, int C, int groups, int window, int transpose,
+                                      void* out_bf16, b200_stream_t stream) {
+  B200_REQUIRE(w_grouped && out_bf16 && K > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && K % groups == 0,
+               B200_ERR_INVALID, "group_weight_pack: bad argument");
+  B200_REQUIRE(window > 0 && window % (C / groups) == 0 && window % (K / groups) == 0 && (window == C || (C == K && C % window == 0)),
+               B200_ERR_UNSUPPORTED, "group_weight_pack: window %d must be a multiple of the group width and divide C == K",
+               window);
+  const long long total = (long long)(transpose ? C : K) * T * window;
+  b200::group_pack_kernel<<<b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_grouped, K, T, C, groups, window, transpose, (__nv_bfloat16*)out_bf16);
+  B200_CHECK_LAUNCH("group_pack_kernel");
   return B200_OK;
 }
 
-extern "C" int b200_group_wgrad_extract(const float* dw_dense, int K, int T, int C, int groups, float* dw_grouped,
-                                        b200_stream_t stream) {
-  B200_REQUIRE(dw_dense && dw_grouped && K > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && K % groups == 0,
-               B200_ERR_INVALID, "group_wgrad_extract: bad argument");
+extern "C" int b200_group_wgrad_unpack(const float* dw_win, int K, int T, int C, int groups, int window, float* dw_grouped,
+                                       b200_stream_t stream) {
+  B200_REQUIRE(dw_win && dw_grouped && K > 0 && T > 0 && C > 0 && groups > 0 && C % groups == 0 && K % groups == 0 &&
+                   window > 0 && window % (C / groups) == 0,
+               B200_ERR_INVALID, "group_wgrad_unpack: bad argument");
   const long long total = (long long)K * T * (C / groups);
-  b200::group_extract_kernel<<<b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_dense, K, T, C, groups,
-                                                                                        dw_grouped);
-  B200_CHECK_LAUNCH("group_extract_kernel");
+  b200::group_unpack_kernel<<<b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_win, K, T, C, groups, window,
+                                                                                       dw_grouped);
+  B200_CHECK_LAUNCH("group_unpack_kernel");
   return B200_OK;
 }

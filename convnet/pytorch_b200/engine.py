@@ -169,6 +169,10 @@ class _Conv(object):
                 raise B200Error('conv %s: bias is only supported on depthwise convolutions followed by BatchNorm' % s.name)
             self.bias32 = arena.kernel_view(arena.p32, arena.slot(mod.bias))
         self.groups = mod.groups if s.kind == 'conv' else 1
+        # grouped convolutions (ResNeXt) run block-diagonally: 64-channel windows for fprop / dgrad, 128 for wgrad
+        # (b200_conv_desc.window); shapes outside that fall back to the dense block-diagonal expansion (window == C)
+        cg = self.C // max(self.groups, 1)
+        self.window = 64 if (self.groups > 1 and self.C == self.K and self.C % 128 == 0 and 64 % cg == 0) else 0
         self.slot = s
         self.wt = None           # [C, R*S, K] view of the runtime's transposed shadow (dgrad operand), set by Runtime
         arena.convs.append(self)
@@ -176,16 +180,23 @@ class _Conv(object):
         self.w32 = arena.kernel_view(arena.p32, s)
         self.g32 = arena.kernel_view(arena.g32, s)
 
-    def desc(self, N, H, W):
+    def desc(self, N, H, W, wgrad=False):
         return ops.make_desc(N, H, W, self.C, self.K, self.R, self.S, self.stride, self.pad,
-                             algo_macs=self.K * self.R * self.S * self.C // self.groups)
+                             algo_macs=self.K * self.R * self.S * self.C // self.groups,
+                             window=(128 if wgrad else 64) if self.window else 0)
 
-    def kernel_weights(self):
-        """bf16 [K, R*S, C] operand of the dense kernels: the arena shadow, or for a grouped convolution the
-        block-diagonal expansion of the fp32 master (zeros outside each output channel's group)."""
+    def kernel_weights(self, w32=None):
+        """bf16 operand of the convolution kernels: the arena shadow [K, R*S, C], or for a grouped convolution the
+        block-diagonal packing of the fp32 master at window granularity ([K, R*S, 64]; dense [K, R*S, C] fallback)."""
         if self.groups == 1:
             return self.w16
-        return ops.group_weight_expand(self.w32, self.K, self.R * self.S, self.C, self.groups)
+        return ops.group_weight_pack(self.w32 if w32 is None else w32, self.K, self.R * self.S, self.C, self.groups,
+                                     self.window or self.C)
+
+    def dgrad_weights(self):
+        """grouped convolutions: [C, R*S, window] operand of dgrad, packed from the fp32 master."""
+        return ops.group_weight_pack(self.w32, self.K, self.R * self.S, self.C, self.groups, self.window or self.C,
+                                     transpose=True)
 
 
 class _BN(object):
@@ -338,7 +349,7 @@ class Runtime(object):
         if conv.groups == 1:
             wf = w32.to(torch.bfloat16).contiguous()
         else:
-            wf = ops.group_weight_expand(w32.contiguous(), conv.K, conv.R * conv.S, conv.C, conv.groups)
+            wf = conv.kernel_weights(w32.contiguous())
         self._fold_cache[key] = (self.arena.version, wf, shift)
         return wf, shift
 
@@ -493,16 +504,21 @@ class Runtime(object):
         conv = u.conv
         if conv.groups == 1:
             self._wgrad_async(lambda: ops.conv_wgrad(u.x, dz, u.desc, conv.g32), u.x, dz)
-        else:  # dense wgrad into a scratch, then keep the diagonal (group) blocks
+        else:  # windowed (block-diagonal) wgrad into a scratch [K, T, window], then keep each channel's group
             def grouped():
                 T = conv.R * conv.S
-                dense = torch.zeros((conv.K, T, conv.C), device=self.device, dtype=torch.float32)
-                ops.conv_wgrad(u.x, dz, u.desc, dense)
-                ops.group_wgrad_extract(dense, conv.K, T, conv.C, conv.groups, conv.g32)
+                N, H, W, _ = u.x.shape
+                win = 128 if conv.window else conv.C
+                scratch = torch.zeros((conv.K, T, win), device=self.device, dtype=torch.float32)
+                ops.conv_wgrad(u.x, dz, conv.desc(N, H, W, wgrad=True), scratch)
+                ops.group_wgrad_unpack(scratch, conv.K, T, conv.C, conv.groups, win, conv.g32)
             self._wgrad_async(grouped, u.x, dz)
         if not need_dx:
             return None
-        wt = conv.wt if (conv.wt is not None and self._wt_jobs is not None) else ops.weight_transpose(u.w)
+        if conv.groups > 1:
+            wt = conv.dgrad_weights()
+        else:
+            wt = conv.wt if (conv.wt is not None and self._wt_jobs is not None) else ops.weight_transpose(u.w)
         return ops.conv_dgrad(dz, wt, u.desc, residual=residual)
 
     # ---- classifier head: global average pool -> (dropout) -> linear as a 1x1 conv on a 1x1 map ----------

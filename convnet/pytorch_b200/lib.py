@@ -21,7 +21,7 @@ class B200Error(RuntimeError):
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ("N", "H", "W", "C", "K", "R", "S", "stride", "pad_h", "pad_w", "P", "Q",
-                 "x_pixel_stride", "x_row_stride", "x_image_stride")]
+                 "x_pixel_stride", "x_row_stride", "x_image_stride", "window")]
 
 
 class Epilogue(ctypes.Structure):
@@ -61,8 +61,8 @@ SIGNATURES = {
     "b200_stem_weight_to_s2d": [_vp, _i, _i, _i, _vp, _vp],
     "b200_stem_wgrad_from_s2d": [_vp, _i, _i, _i, _vp, _vp],
     "b200_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
-    "b200_group_weight_expand": [_vp, _i, _i, _i, _i, _vp, _vp],
-    "b200_group_wgrad_extract": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "b200_group_weight_pack": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "b200_group_wgrad_unpack": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
     "b200_se_pool": [_vp, _i, _i, _i, _vp, _vp],
     "b200_se_scale_fwd": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "b200_se_bwd_reduce": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],

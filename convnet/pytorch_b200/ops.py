@@ -88,11 +88,11 @@ def out_size(h, r, stride, pad_lo, pad_hi=None):
     return (h + pad_lo + pad_hi - r) // stride + 1
 
 
-def make_desc(N, H, W, C, K, R, S, stride, pad, P=None, Q=None, x_strides=(0, 0, 0), algo_macs=None):
+def make_desc(N, H, W, C, K, R, S, stride, pad, P=None, Q=None, x_strides=(0, 0, 0), algo_macs=None, window=0):
     pad_h, pad_w = (pad, pad) if isinstance(pad, int) else pad
     P = out_size(H, R, stride, pad_h) if P is None else P
     Q = out_size(W, S, stride, pad_w) if Q is None else Q
-    d = ConvDesc(N, H, W, C, K, R, S, stride, pad_h, pad_w, P, Q, *x_strides)
+    d = ConvDesc(N, H, W, C, K, R, S, stride, pad_h, pad_w, P, Q, *x_strides, int(window))
     if algo_macs is not None:
         d.algo_macs = int(algo_macs)      # python-side annotation only (not part of the C struct)
     return d
@@ -413,20 +413,21 @@ def stem_wgrad_from_s2d(dw_s2d, K, C, cpad, dw):
     return dw
 
 
-def group_weight_expand(w32_grouped, K, T, C, groups, out=None):
-    """fp32 [K,T,C/g] -> block-diagonal dense bf16 [K,T,C]."""
+def group_weight_pack(w32_grouped, K, T, C, groups, window, transpose=False, out=None):
+    """fp32 [K,T,C/g] -> bf16 [K,T,window] (or [C,T,window] transposed): the block-diagonal operand of a grouped
+    convolution at window granularity (window == C: dense expansion)."""
     if out is None:
-        out = torch.empty((K, T, C), device=w32_grouped.device, dtype=bf16)
+        out = torch.empty((C if transpose else K, T, window), device=w32_grouped.device, dtype=bf16)
     with _T('weight_transpose', 0, 2 * out.numel()):
-        _l.check(_l.load().b200_group_weight_expand(w32_grouped.data_ptr(), K, T, C, groups, out.data_ptr(), _stream()),
-                 "b200_group_weight_expand")
+        _l.check(_l.load().b200_group_weight_pack(w32_grouped.data_ptr(), K, T, C, groups, int(window), int(bool(transpose)),
+                                                  out.data_ptr(), _stream()), "b200_group_weight_pack")
     return out
 
 
-def group_wgrad_extract(dw_dense, K, T, C, groups, dw_grouped):
+def group_wgrad_unpack(dw_win, K, T, C, groups, window, dw_grouped):
     with _T('weight_transpose', 0, 4 * dw_grouped.numel()):
-        _l.check(_l.load().b200_group_wgrad_extract(dw_dense.data_ptr(), K, T, C, groups, dw_grouped.data_ptr(),
-                                                    _stream()), "b200_group_wgrad_extract")
+        _l.check(_l.load().b200_group_wgrad_unpack(dw_win.data_ptr(), K, T, C, groups, int(window), dw_grouped.data_ptr(),
+                                                   _stream()), "b200_group_wgrad_unpack")
     return dw_grouped
 
 

@@ -64,7 +64,8 @@ def _bn(x, sd, prefix, training, buffers_out, quant):
 
 def _conv(x, sd, name, stride, padding, quant):
     w = sd[name + '.weight']
-    return _q(F.conv2d(x, w, None, stride=stride, padding=padding, groups=x.size(1) // w.size(1)), quant)
+    # a convolution bias exists only in MobileNet-v1's depthwise layers (models/mobilenet.py:44-46 of the reference)
+    return _q(F.conv2d(x, w, sd.get(name + '.bias'), stride=stride, padding=padding, groups=x.size(1) // w.size(1)), quant)
 
 
 def _block_names(sd, layer):
@@ -119,7 +120,9 @@ def _mb_conv_bn(x, sd, conv, bn, stride, pad, act, training, bufs, quant, skip=N
     kernel pipeline: after the conv and after the BN/activation(/add) pass."""
     z = _conv(x, sd, conv, stride, pad, quant)          # groups inferred from the weight shape (depthwise: C/1)
     y = _bn(z, sd, bn, training, bufs, quant)
-    if act:
+    if act == 'relu':
+        y = F.relu(y)
+    elif act:
         y = F.relu6(y)
     if skip is not None:
         y = y + skip
@@ -129,6 +132,25 @@ def _mb_conv_bn(x, sd, conv, bn, stride, pad, act, training, bufs, quant, skip=N
     return y
 
 
+# strides of MobileNet-v1's 13 depthwise-separable units (models/mobilenet.py:70-112; the shallow variant drops 5)
+_MBV1_STRIDES = (1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1)
+
+
+def forward_mobilenet_v1(sd, x, training=True, buffers_out=None, quant=False, trace=None):
+    """logits of a reference-layout MobileNet (v1) ``state_dict`` (models/mobilenet.py:39-156): stem conv/BN/ReLU, then
+    ``features.{i}.components`` = depthwise 3x3 (with bias) / BN / ReLU / 1x1 / BN / ReLU, average pool, ``fc``."""
+    x = _q(x, quant)
+    x = _mb_conv_bn(x, sd, 'features.0', 'features.1', 2, 1, 'relu', training, buffers_out, quant, trace=trace)
+    idx = sorted({int(m.group(1)) for k in sd for m in [re.match(r'features\.(\d+)\.components\.', k)] if m})
+    strides = _MBV1_STRIDES if len(idx) == 13 else tuple(s for j, s in enumerate(_MBV1_STRIDES) if not 6 <= j <= 10)
+    for j, i in enumerate(idx):
+        p = 'features.%d.components' % i
+        x = _mb_conv_bn(x, sd, p + '.0', p + '.1', strides[j], 1, 'relu', training, buffers_out, quant, trace=trace)
+        x = _mb_conv_bn(x, sd, p + '.3', p + '.4', 1, 0, 'relu', training, buffers_out, quant, trace=trace)
+    x = _q(x.mean((2, 3)), quant)
+    return F.linear(x, sd['fc.weight'], sd['fc.bias'])
+
+
 def mobilenet_v2_unit_trace(sd, x, y, quant=True):
     """Teacher-forcing data for unit-level parity: every conv+BN(+ReLU6)(+skip) unit of one training forward/backward
     with its input ``x``, skip input, output ``y`` and the gradient ``dy`` arriving at its output (all detached).
@@ -136,7 +158,10 @@ def mobilenet_v2_unit_trace(sd, x, y, quant=True):
     activations and gradients, the comparison is well posed."""
     work = {k: (v.detach().clone().requires_grad_(True) if k in param_names(sd) else v) for k, v in sd.items()}
     trace = []
-    logits = forward_mobilenet_v2(work, x, True, {}, quant, 0.0, trace=trace)
+    if 'features.conv0.0.weight' in sd:
+        logits = forward_mobilenet_v2(work, x, True, {}, quant, 0.0, trace=trace)
+    else:
+        logits = forward_mobilenet_v1(work, x, True, {}, quant, trace=trace)
     loss = cross_entropy(logits, y)
     dys = torch.autograd.grad(loss, [u['y'] for u in trace])
     units = []
@@ -151,6 +176,8 @@ def mobilenet_v2_unit_vjp(sd, unit, quant=True, dtype=torch.float64):
     respect to the unit input, the conv weight and the BN affine parameters (same storage roundings as the net)."""
     x = unit['x'].to(dtype).requires_grad_(True)
     names = [unit['conv'] + '.weight', unit['bn'] + '.weight', unit['bn'] + '.bias']
+    if unit['conv'] + '.bias' in sd:
+        names.append(unit['conv'] + '.bias')
     local = {k: v for k, v in sd.items() if k.startswith(unit['conv'] + '.') or k.startswith(unit['bn'] + '.')}
     local = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in local.items()}
     for n in names:
@@ -159,7 +186,7 @@ def mobilenet_v2_unit_vjp(sd, unit, quant=True, dtype=torch.float64):
     yy = _mb_conv_bn(x, local, unit['conv'], unit['bn'], unit['stride'], unit['pad'], unit['act'], True, None, quant,
                      skip=skip)
     grads = torch.autograd.grad(yy, [x] + [local[n] for n in names], unit['dy'].to(dtype))
-    return yy.detach(), grads[0], grads[1], grads[2], grads[3]
+    return (yy.detach(),) + tuple(grads)          # y, dx, dW, dgamma, dbeta [, dbias of the convolution]
 
 
 def forward_mobilenet_v2(sd, x, training=True, buffers_out=None, quant=False, dropout_p=0.0, trace=None):
@@ -195,6 +222,8 @@ def forward(sd, x, training=True, buffers_out=None, quant=False, dropout_p=0.0):
     ResNeXt, whose grouped convolutions are inferred from the weight shapes) or MobileNet-v2."""
     if 'features.conv0.0.weight' in sd:
         return forward_mobilenet_v2(sd, x, training, buffers_out, quant, dropout_p)
+    if 'features.0.weight' in sd:
+        return forward_mobilenet_v1(sd, x, training, buffers_out, quant)
     x = _q(x, quant)
     imagenet = sd['conv1.weight'].shape[-1] == 7
     if imagenet:

@@ -402,3 +402,15 @@ def test_conv_fprop_dgrad_wgrad(case):
         assert r.get('transpose_ok', True), r
         assert r['dgrad'][0] < 4e-3, r
     assert r['wgrad'][0] < 2e-5 and r['wgrad_acc'][0] < 2e-5, r
+
+
+@pytest.mark.parametrize("case", ["g32_128_56", "g32_256_28s2", "g32_512_14", "g32_1024_7", "g8_256_20x12"])
+def test_grouped_conv_window_mode(case):
+    """Grouped 3x3 convolutions (nn.Conv2d(groups=32) of models/resnext.py:10-16) as block-diagonal 64-channel windows
+    (b200_conv_desc.window): fprop / dgrad / wgrad vs F.conv2d(groups=g) in fp64 on bf16-rounded operands, same
+    tolerances as the dense kernels; the dense block-diagonal expansion must give the same output."""
+    diag = _conv_cases()
+    r = diag.run_grouped(case)
+    assert r['fprop'][0] < 4e-3 and r['dgrad'][0] < 4e-3, r
+    assert r['wgrad'][0] < 2e-5, r
+    assert r['dense_vs_window'][0] < 4e-3, r

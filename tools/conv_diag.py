@@ -52,6 +52,56 @@ CASES = {
 }
 
 
+# grouped 3x3 convolutions (ResNeXt 32 groups) through the block-diagonal "window" mode: (N,H,W,C=K,stride,groups)
+GROUPED = {
+    "g32_128_56": (2, 56, 56, 128, 1, 32),      # C/g = 4, halo kernels (fprop/dgrad window 64, wgrad window 128)
+    "g32_256_28s2": (2, 28, 28, 256, 2, 32),    # stride 2: im2col igemm + im2col wgrad, 4 dgrad residue classes
+    "g32_512_14": (3, 14, 14, 512, 1, 32),      # C/g = 16
+    "g32_1024_7": (4, 7, 7, 1024, 1, 32),       # 7x7 maps: im2col path, C/g = 32
+    "g8_256_20x12": (2, 20, 12, 256, 1, 8),     # C/g = 32, non-square map
+}
+
+
+def run_grouped(name):
+    from convnet.pytorch_b200 import ops
+    N, H, W, C, stride, groups = GROUPED[name]
+    K, cg, T = C, C // groups, 9
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(4321)
+    x = torch.randn(N, H, W, C, generator=g).to(dev).to(torch.bfloat16)
+    wg = (torch.randn(K, T, cg, generator=g) / (T * cg) ** 0.5).to(dev)
+    wg = wg.to(torch.bfloat16).float()                                   # fp32 master with bf16-exact values
+    d64 = ops.make_desc(N, H, W, C, K, 3, 3, stride, 1, window=64)
+    d128 = ops.make_desc(N, H, W, C, K, 3, 3, stride, 1, window=128)
+    P, Q = d64.P, d64.Q
+    xd = x.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wd = wg.double().view(K, 3, 3, cg).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    yref = F.conv2d(xd, wd, None, stride=stride, padding=1, groups=groups)
+    out = {"case": name}
+    w64 = ops.group_weight_pack(wg, K, T, C, groups, 64)
+    y = ops.conv_fprop(x, w64, d64)
+    torch.cuda.synchronize()
+    out["fprop"] = rel_err(y.permute(0, 3, 1, 2), yref.detach())
+    dy = torch.randn(N, P, Q, K, generator=g).to(dev).to(torch.bfloat16)
+    gx, gw = torch.autograd.grad(yref, [xd, wd], dy.double().permute(0, 3, 1, 2))
+    wt64 = ops.group_weight_pack(wg, K, T, C, groups, 64, transpose=True)
+    dx = ops.conv_dgrad(dy, wt64, d64)
+    torch.cuda.synchronize()
+    out["dgrad"] = rel_err(dx.permute(0, 3, 1, 2), gx)
+    scratch = torch.zeros(K, T, 128, device=dev, dtype=torch.float32)
+    ops.conv_wgrad(x, dy, d128, scratch)
+    dwg = torch.zeros(K, T, cg, device=dev, dtype=torch.float32)
+    ops.group_wgrad_unpack(scratch, K, T, C, groups, 128, dwg)
+    torch.cuda.synchronize()
+    out["wgrad"] = rel_err(dwg, gw.permute(0, 2, 3, 1).reshape(K, T, cg))
+    # the dense expansion (window == C) must agree with the windowed result
+    wfull = ops.group_weight_pack(wg, K, T, C, groups, C)
+    y2 = ops.conv_fprop(x, wfull, ops.make_desc(N, H, W, C, K, 3, 3, stride, 1))
+    torch.cuda.synchronize()
+    out["dense_vs_window"] = rel_err(y2, y)
+    return out
+
+
 def rel_err(a, b):
     a = a.double(); b = b.double()
     return float((a - b).norm() / (b.norm() + 1e-30)), float((a - b).abs().max()), float(b.abs().max())
@@ -124,7 +174,7 @@ if __name__ == "__main__":
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
-            r = run(sys.argv[1])
+            r = run_grouped(sys.argv[1]) if sys.argv[1] in GROUPED else run(sys.argv[1])
             ok = all(v[0] < 1e-2 for k, v in r.items() if isinstance(v, tuple))
             r["ok"] = ok
             print("DIAG " + json.dumps(r))
