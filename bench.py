@@ -92,6 +92,10 @@ class ClockSampler(threading.Thread):
                 'power_w_max': max(float(s[2]) for s in self.samples), 'samples': len(self.samples)}
 
 
+def default_cfg_for_traffic(args):
+    return args.model == 'resnet' and args.depth == 50 and args.size == IMG and args.batch == 256
+
+
 def usable_cores():
     """host threads this process may actually use: affinity mask capped by the cgroup CPU quota."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
@@ -326,6 +330,18 @@ def main():
             ach = d['bytes'] / (d['ms'] * 1e-3) / 1e9
             roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                     'frac': ach / pk['hbm_gbs'], 'traffic': None}
+        # traffic: DRAM bytes (ncu dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant class, from
+        # the committed launch list of this same command (profiles/r02_traffic.json; tools/profile_round2.sh)
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
+                tj = json.load(f)['classes']
+            key = dom if dom in tj else ('conv_fprop+dgrad' if dom in ('conv_fprop', 'conv_dgrad') else None)
+            if key and default_cfg_for_traffic(args):
+                roof['traffic'] = (tj[key]['dram_read_bytes'] + tj[key]['dram_write_bytes']) / max(tj[key]['launches'], 1)
+                roof['traffic_unit'] = 'bytes per launch (class average; ncu, profiles/r02_traffic.json)'
+                roof['algorithmic_bytes_per_launch'] = None
+        except Exception:
+            pass
         roof['peak_source'] = pk['source'] + (' sustained' if dom.startswith('conv_') else '')
         roof['launches_of_kernel_per_step'] = d['calls']
         roof['avg_launch_ms'] = d['ms'] / max(d['calls'], 1)

@@ -281,6 +281,11 @@ class Runtime(object):
                                      # .finish() at the end of the backward pass
         self._bucket_hi = None
         self._bucket_min = int(os.environ.get('B200_BUCKET_MIN_ELEMS', 1 << 20))
+        # SyncBatchNorm (main.py:190-191 of the reference: nn.SyncBatchNorm.convert_sync_batchnorm): with sync_bn set
+        # (engine.enable_sync_batchnorm) the per-channel sum / sum^2 accumulated by the conv epilogue are all-reduced over
+        # the ranks before the statistics are finalised, and d gamma / d beta sums before the BN input gradient
+        self.sync_bn_group = None
+        self.sync_bn_world = 1
         self._fused_dl = None        # bf16 dlogits handed from _FusedCE.backward to run_backward (side channel)
         self._ce_dummy = torch.zeros((), device=device, dtype=torch.float32)
         self._build()
@@ -405,8 +410,17 @@ class Runtime(object):
         u.mean, u.invstd, u.scale, u.shift, u.sums = buf[0:C], buf[C:2 * C], buf[2 * C:3 * C], buf[3 * C:4 * C], \
             buf[4 * C:6 * C]
         m = bn.mod
+        if training and self.sync_bn_world > 1 and not fused:
+            raise B200Error('SyncBatchNorm on the B200 path needs the conv-epilogue statistics (output channels % 64 == 0)')
         if training and fused:
-            ops.bn_finalize(u.z.numel() // C, C, bn.gamma, bn.beta, m.eps, m.momentum, m.running_mean, m.running_var,
+            M = u.z.numel() // C
+            if self.sync_bn_world > 1:
+                # the epilogue accumulators are fp64 [16 replicas][2][C] at the start of the BN workspace: ONE small
+                # all-reduce makes them global sums; the statistics then are those of the global batch
+                import torch.distributed as dist
+                dist.all_reduce(self._ws.view(torch.float64)[:16 * 2 * C], group=self.sync_bn_group)
+                M *= self.sync_bn_world
+            ops.bn_finalize(M, C, bn.gamma, bn.beta, m.eps, m.momentum, m.running_mean, m.running_var,
                             m.num_batches_tracked, u.mean, u.invstd, u.scale, u.shift, self._ws)
         elif training:
             ops.bn_stats(u.z, bn.gamma, bn.beta, m.eps, m.momentum, m.running_mean, m.running_var,
@@ -443,6 +457,13 @@ class Runtime(object):
         mask = getattr(u, 'mask', None) if y_mask is not None else None
         ops.bn_bwd_reduce(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, bn.dgamma, bn.dbeta,
                           self._ws, act_mask=mask)
+        if self.sync_bn_world > 1:
+            # the input gradient needs the GLOBAL d gamma / d beta sums divided by the global pixel count; the kernel
+            # divides by the local count, so the reduced sums are pre-scaled by 1/world (equal per-rank batches).  The
+            # arena gradients received the local sums above and are averaged with all other gradients later.
+            import torch.distributed as dist
+            dist.all_reduce(u.sums, group=self.sync_bn_group)
+            u.sums.mul_(1.0 / self.sync_bn_world)
         g = torch.empty_like(dy) if want_g else None
         dz = ops.bn_bwd_dx(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, g_out=g, act_mask=mask)
         return dz, g
@@ -1013,6 +1034,24 @@ class MobileNetV1Runtime(MobileNetRuntime):
         self._head_build(m.fc, dropout_p=0.0)
         max_c = max(u[1].C for b in self.blocks for u in b['units'] if u[0] == 'dw')
         self._dw_ws = torch.empty(592 * 9 * max_c, device=self.device, dtype=torch.float32)
+
+
+def enable_sync_batchnorm(model, process_group=None):
+    """SyncBatchNorm for a converted model (``--sync-bn``, main.py:82-83,190-191 of the reference): batch statistics and
+    the BN backward sums are taken over all ranks of ``process_group`` (equal per-rank batches assumed, as with
+    DistributedSampler).  Two small all-reduces per BN layer and step; every layer's output width must allow the fused
+    conv-epilogue statistics (multiples of 64 channels)."""
+    import torch.distributed as dist
+    rt = getattr(model, '_b200', None)
+    if rt is None:
+        raise B200Error('enable_sync_batchnorm needs a model converted by convert_b200')
+    if not (dist.is_available() and dist.is_initialized()):
+        raise B200Error('enable_sync_batchnorm needs an initialised process group')
+    if not FUSE_BN_STATS:
+        raise B200Error('SyncBatchNorm needs B200_FUSE_BN_STATS=1 (statistics accumulated by the conv epilogue)')
+    rt.sync_bn_group = process_group
+    rt.sync_bn_world = dist.get_world_size(process_group)
+    return model
 
 
 def convert_b200(model, device=None):

@@ -62,7 +62,7 @@ def build_parser():
     a('--drop-optim-state', action='store_true', default=False, help='do not save optimizer state for resume')
     a('--save-all', action='store_true', default=False, help='save checkpoint for every epoch')
     a('--label-smoothing', default=0, type=float, help='label smoothing coefficient')
-    a('--sync-bn', action='store_true', default=False, help='synchronize batch-norm (torch path only)')
+    a('--sync-bn', action='store_true', default=False, help='synchronize batch-norm statistics across ranks')
     a('--mixup', default=None, type=float, help='mixup alpha coefficient (not supported)')
     a('--cutmix', default=None, type=float, help='cutmix alpha coefficient (not supported)')
     a('--duplicates', default=1, type=int, help='number of augmentations over single example')
@@ -159,9 +159,7 @@ def main_worker(args):
     if args.model_config != '':
         model_config = dict(model_config, **literal_eval(args.model_config))
     model = models.__dict__[args.model](**model_config)
-    if args.sync_bn:
-        if use_b200:
-            raise NotImplementedError('--sync-bn is not available on the B200 path (per-rank BN statistics)')
+    if args.sync_bn and not use_b200:
         model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
     logging.info('created model with configuration: %s', model_config)
     logging.info('number of parameters: %d', sum(p.nelement() for p in model.parameters()))
@@ -194,6 +192,9 @@ def main_worker(args):
     if use_b200:
         from .engine import convert_b200
         model = convert_b200(model, args.device)   # fp32 masters in the arena, bf16 compute inside the kernels
+        if args.sync_bn and args.distributed:
+            from .engine import enable_sync_batchnorm
+            enable_sync_batchnorm(model)             # statistics all-reduced between the conv epilogue and bn_finalize
         criterion.to(args.device)
     else:
         criterion.to(args.device, dtype)

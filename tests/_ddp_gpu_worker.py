@@ -6,7 +6,9 @@ Checks, on the real multi-GPU path of Trainer (flat arena, bucketed NCCL all-red
   2. one step: the reduced gradient arena equals the SUM of the per-rank local gradients (so SGD's 1/world gives the
      mean), bit for bit on every rank;
   3. after 3 more steps through Trainer.train (eager warm-up, CUDA-graph capture with the all-reduce inside, replay)
-     the parameters are bit-identical on all ranks; BN running statistics are per rank by design.
+     the parameters are bit-identical on all ranks; BN running statistics are per rank by design (SURVEY 2.3 C2);
+  4. SyncBatchNorm (engine.enable_sync_batchnorm, --sync-bn): W ranks x B samples give the statistics, logits and
+     (averaged) gradients of ONE process running the W*B batch.
 Prints one line 'DDP_CHECK OK ...' on rank 0 or raises."""
 import os
 import sys
@@ -83,10 +85,37 @@ def main():
     assert not torch.equal(ps[0], want.new_zeros(()).expand_as(ps[0])), 'parameters are zero'
     rm = gather(model.bn1.running_mean)
     per_rank_bn = not all(torch.equal(rm[0], t) for t in rm)
+    # 4. SyncBatchNorm: this rank's 16 samples with synchronised statistics vs the concatenated batch in one process
+    from convnet.pytorch_b200.engine import enable_sync_batchnorm
+    torch.manual_seed(7)
+    m_sync = convert_b200(models.resnet(dataset='imagenet', depth=18), dev)
+    torch.manual_seed(7)
+    m_full = convert_b200(models.resnet(dataset='imagenet', depth=18), dev)
+    enable_sync_batchnorm(m_sync)
+    gs = torch.Generator().manual_seed(555)
+    xs = torch.randn(16 * world, 3, 64, 64, generator=gs).to(dev)
+    ys = torch.randint(0, 1000, (16 * world,), generator=gs).to(dev)
+    m_sync.train(); m_full.train()
+    lo_s, _ = m_sync._b200.train_step(xs[16 * rank:16 * rank + 16], ys[16 * rank:16 * rank + 16], 0.0, None)
+    g_sync = m_sync._b200.arena.g32.clone()
+    dist.all_reduce(g_sync)
+    g_sync /= world
+    lo_f, _ = m_full._b200.train_step(xs, ys, 0.0, None)
+    torch.cuda.synchronize()
+    g_full = m_full._b200.arena.g32
+
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+    r_log = rel(lo_s, lo_f[16 * rank:16 * rank + 16])
+    r_rm = max(rel(a, b) for (n, a), (_, b) in zip(m_sync.named_buffers(), m_full.named_buffers()) if 'running' in n)
+    r_g = rel(g_sync, g_full)
+    assert r_log < 2e-3 and r_rm < 1e-4 and r_g < 2e-2, 'SyncBatchNorm: logits %.3e running stats %.3e grads %.3e' % (
+        r_log, r_rm, r_g)
     if rank == 0:
-        print('DDP_CHECK OK world=%d steps=%d graph_replays=%d buckets_per_step=%s loss=%.4f per_rank_bn_stats=%s'
-              % (world, tr.training_steps, tr.graph_replays, getattr(hook, 'launched', 0), res['loss'], per_rank_bn),
-              flush=True)
+        print('DDP_CHECK OK world=%d steps=%d graph_replays=%d buckets_per_step=%s loss=%.4f per_rank_bn_stats=%s '
+              'syncbn(logits %.2e stats %.2e grads %.2e)'
+              % (world, tr.training_steps, tr.graph_replays, getattr(hook, 'launched', 0), res['loss'], per_rank_bn,
+                 r_log, r_rm, r_g), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

