@@ -380,8 +380,24 @@ def main():
                                           / (world * peaks()['tflops'])) if default_cfg else None}
         print(json.dumps(line), flush=True)
     if distributed:
+        shutdown(trainer)
+
+
+def shutdown(trainer):
+    """Leave a multi-rank run promptly: captured graphs released first (they hold NCCL work), then barrier + destroy, with
+    a watchdog that hard-exits if the teardown blocks (the JSON line is already printed and flushed)."""
+    def _bail():
+        sys.stdout.flush()
+        os._exit(0)
+    timer = threading.Timer(30.0, _bail)
+    timer.daemon = True
+    timer.start()
+    try:
+        trainer.release_graphs()
         dist.barrier()
         dist.destroy_process_group()
+    finally:
+        timer.cancel()
 
 
 if __name__ == '__main__':

@@ -49,6 +49,9 @@ struct IgemmParams {
   int tma_store;         // 1: dense bf16 output staged in smem and written by TMA (tmC), residual via tmR
   int plain_a;           // 1: A is a dense [M_total, SC] matrix (1x1, stride 1, no padding): tiled TMA
   int b_stationary;      // 1: every (tap, k-block) weight slice stays in shared memory (small 1x1 layers): only A streams
+  int epi_bufs;          // 1 or 2 output staging tiles: with 2 the residual tile of the NEXT tile is fetched while this one
+                         // is converted and stored, and a store never waits for the previous one (write-heavy epilogues)
+  uint32_t epi_bytes;
   int window;            // > 0: block-diagonal convolution -- n-tile b (block_n == window) reads source channels
                          // [window*b, window*b + window) only; the weight operand is [N_total][taps][window]
   double* stats;         // fused BN statistics accumulators [kStatReplicas][2][N_total] (BN workspace) or nullptr
@@ -134,7 +137,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
-  __shared__ __align__(8) uint64_t res_bar, bstat_bar;
+  __shared__ __align__(8) uint64_t res_bar[2], bstat_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
@@ -155,7 +158,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 8);
     mbar_init(&tmem_empty[1], 8);
-    mbar_init(&res_bar, 1);
+    mbar_init(&res_bar[0], 1);
+    mbar_init(&res_bar[1], 1);
     fence_mbar_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -292,17 +296,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // clipped at the M tail); the residual tile is fetched by TMA into the same buffer and updated in place.
         const bool leader = (warp == 2 && lane == 0);
         const int row = q * 32 + lane;
-        uint8_t* epi = epi_base;
         const int nbox = p.block_n >> 6;
-        if (leader && local > 0) bulk_wait_group_read0();  // previous tile's store has finished reading smem
+        // staging buffer of this tile; with two buffers tile i uses buffer i & 1
+        const int eb = p.epi_bufs == 2 ? (local & 1) : 0;
+        uint8_t* epi = epi_base + eb * p.epi_bytes;
+        if (leader) {
+          // the buffer about to be (re)written must no longer be read by an earlier TMA store: one buffer -> the
+          // previous store; two buffers -> the store before the previous one, unless the NEXT tile's residual is
+          // prefetched below into the buffer the previous store used
+          if (local > 0) {
+            if (p.epi_bufs == 2 && p.res == nullptr) { if (local > 1) bulk_wait_group_read1(); }
+            else bulk_wait_group_read0();
+          }
+          if (p.res != nullptr) {
+            auto fetch = [&](int t_tile, int buf) {
+              const int mt = t_tile / p.n_tiles, nt = t_tile - mt * p.n_tiles;
+              uint8_t* dst = epi_base + buf * p.epi_bytes;
+              mbar_arrive_expect_tx(&res_bar[buf], static_cast<uint32_t>(nbox) * kTileM * 128u);
+              for (int b = 0; b < nbox; ++b)
+                tma_load_2d(&tmR, &res_bar[buf], dst + b * (kTileM * 128), nt * p.block_n + b * 64, mt * kTileM);
+            };
+            if (p.epi_bufs == 2) {
+              if (local == 0) fetch(tile, 0);
+              const int next = tile + static_cast<int>(gridDim.x);
+              if (next < total_tiles) fetch(next, eb ^ 1);      // lands while this tile is converted and stored
+            } else {
+              fetch(tile, 0);
+            }
+          }
+        }
         named_bar_sync(1, 256);
         if (p.res != nullptr) {
-          if (leader) {
-            mbar_arrive_expect_tx(&res_bar, static_cast<uint32_t>(nbox) * kTileM * 128u);
-            for (int b = 0; b < nbox; ++b)
-              tma_load_2d(&tmR, &res_bar, epi + b * (kTileM * 128), nbase + b * 64, m_tile * kTileM);
-          }
-          mbar_wait(&res_bar, static_cast<uint32_t>(local & 1));
+          // buffer b receives tiles b, b+2, b+4, ... (two buffers) or every tile (one buffer): k-th use -> parity k & 1
+          const uint32_t use = p.epi_bufs == 2 ? static_cast<uint32_t>(local >> 1) : static_cast<uint32_t>(local);
+          mbar_wait(&res_bar[eb], use & 1u);
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -847,7 +874,13 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     bstat_bytes = b_all;
     stage = p.a_bytes;
   }
-  p.num_stages = (kSmemBudget - epi_bytes - bstat_bytes) / (int)stage;
+  // second staging tile (residual prefetch, store/convert overlap) whenever at least three operand stages remain
+  static const bool epi2_enabled = !(getenv("B200_IGEMM_EPI2") && atoi(getenv("B200_IGEMM_EPI2")) == 0);
+  p.epi_bufs = 1;
+  p.epi_bytes = (uint32_t)epi_bytes;
+  if (epi2_enabled && p.tma_store && (kSmemBudget - 2 * epi_bytes - bstat_bytes) / (int)stage >= 3) p.epi_bufs = 2;
+  const int epi_total = epi_bytes * p.epi_bufs;
+  p.num_stages = (kSmemBudget - epi_total - bstat_bytes) / (int)stage;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (p.num_stages < 2) p.num_stages = 2;
   p.OH = L.OH; p.OW = L.OW; p.os = L.os; p.oh0 = L.oh0; p.ow0 = L.ow0; p.ldo = L.ldo;
@@ -886,7 +919,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  const int smem_bytes = p.num_stages * (int)stage + bstat_bytes + epi_bytes + 1024;
+  const int smem_bytes = p.num_stages * (int)stage + bstat_bytes + epi_total + 1024;
   rc = set_smem_attr((const void*)conv_igemm_kernel, smem_bytes);
   if (rc) return rc;
   const int total_tiles = p.m_tiles * p.n_tiles;

@@ -281,6 +281,7 @@ def main_worker(args):
         results.add(**values)
         results.save()
     if args.distributed:
+        trainer.release_graphs()       # captured steps hold NCCL work: drop them before the process group goes away
         dist.barrier()
     return last
 

@@ -263,7 +263,10 @@ class Trainer(object):
         n0 = lib.launch_count()
         up = self._upstream()
         eps = self._plain_ce_eps()
-        with torch.cuda.graph(graph, pool=self._graph_pool):
+        # with NCCL all-reduces inside the capture, ProcessGroupNCCL's watchdog thread polls CUDA events concurrently: the
+        # default "global" capture mode would treat that as a capture violation
+        mode = 'thread_local' if self.b200.grad_bucket_hook is not None else 'global'
+        with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode=mode):
             stats = None
             if eps is not None:            # the whole step is library calls: nothing of autograd inside the graph
                 out, stats = self.b200.train_step(x_s, y_s, eps, up)
@@ -273,6 +276,16 @@ class Trainer(object):
                 loss = self.criterion(out, y_s)
                 torch.autograd.backward(loss, grad_tensors=[up])
         st.update(graph=graph, x=x_s, y=y_s, out=out, loss=loss, stats=stats, launches=lib.launch_count() - n0)
+
+    def release_graphs(self):
+        """Drop every captured step (call before tearing the process group down: graphs that captured NCCL all-reduces
+        keep the communicator busy and destroy_process_group() can block on them)."""
+        self._graphs.clear()
+        self._graph_pool = None
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     def _plain_ce_eps(self):
         """label-smoothing coefficient when the criterion is the reference's plain CrossEntropyLoss (class indices,
