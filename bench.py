@@ -389,15 +389,17 @@ def shutdown(trainer):
     def _bail():
         sys.stdout.flush()
         os._exit(0)
-    timer = threading.Timer(30.0, _bail)
+    timer = threading.Timer(20.0, _bail)
     timer.daemon = True
     timer.start()
-    try:
-        trainer.release_graphs()
-        dist.barrier()
-        dist.destroy_process_group()
-    finally:
-        timer.cancel()
+    trainer.release_graphs()
+    dist.barrier()
+    dist.destroy_process_group()
+    # the result line is out and every rank passed the barrier: skip interpreter finalisation (communicator / context
+    # destructors have been seen to block after graphs with captured collectives) -- the timer stays armed until here
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':

@@ -874,11 +874,15 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     bstat_bytes = b_all;
     stage = p.a_bytes;
   }
-  // second staging tile (residual prefetch, store/convert overlap) whenever at least three operand stages remain
-  static const bool epi2_enabled = !(getenv("B200_IGEMM_EPI2") && atoi(getenv("B200_IGEMM_EPI2")) == 0);
+  // second staging tile (residual prefetched one tile ahead, store/convert overlap) when at least three operand
+  // stages remain.  B200_IGEMM_EPI2: 0 = never, 2 = every epilogue, default 1 = epilogues with a residual only --
+  // measured (profiles/r02_summary.md): residual epilogues gain up to 28 %, plain ones lose 0-8 % to the lost stage
+  static const int epi2_mode = getenv("B200_IGEMM_EPI2") ? atoi(getenv("B200_IGEMM_EPI2")) : 1;
   p.epi_bufs = 1;
   p.epi_bytes = (uint32_t)epi_bytes;
-  if (epi2_enabled && p.tma_store && (kSmemBudget - 2 * epi_bytes - bstat_bytes) / (int)stage >= 3) p.epi_bufs = 2;
+  if ((epi2_mode >= 2 || (epi2_mode == 1 && L.res != nullptr)) && p.tma_store &&
+      (kSmemBudget - 2 * epi_bytes - bstat_bytes) / (int)stage >= 3)
+    p.epi_bufs = 2;
   const int epi_total = epi_bytes * p.epi_bufs;
   p.num_stages = (kSmemBudget - epi_total - bstat_bytes) / (int)stage;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;

@@ -65,7 +65,12 @@ def _bn(x, sd, prefix, training, buffers_out, quant):
 def _conv(x, sd, name, stride, padding, quant):
     w = sd[name + '.weight']
     # a convolution bias exists only in MobileNet-v1's depthwise layers (models/mobilenet.py:44-46 of the reference)
-    return _q(F.conv2d(x, w, sd.get(name + '.bias'), stride=stride, padding=padding, groups=x.size(1) // w.size(1)), quant)
+    b, groups = sd.get(name + '.bias'), x.size(1) // w.size(1)
+    if quant and b is not None:
+        # storage model of the kernel path: the bf16 tensor holds the convolution WITHOUT its bias (the bias in front of
+        # a BatchNorm only shifts the batch mean; the kernels add it to the statistics analytically)
+        return _q(F.conv2d(x, w, None, stride=stride, padding=padding, groups=groups), quant) + b.view(1, -1, 1, 1)
+    return _q(F.conv2d(x, w, b, stride=stride, padding=padding, groups=groups), quant)
 
 
 def _block_names(sd, layer):

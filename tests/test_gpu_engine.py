@@ -339,6 +339,8 @@ def _mobilenet_parity(factory, stem_name, size=128, batch=32):
             # reference sums bf16-ROUNDED dz (storage emulation), i.e. pure rounding noise -- we write exact zeros
             assert float(params[cname + '.bias'].grad.abs().max()) == 0.0
             assert float(vjp[5].abs().max()) < 2e-2 * max(1.0, float(dw_ref.abs().max()))
+        if max(got.values()) > 1e-2:
+            print('  unit %s (%s, x %s): %s' % (cname, kind, tuple(u['x'].shape), {k: '%.2e' % v for k, v in got.items()}))
         for k, v in got.items():
             if v > worst.get(k, (0.0, ''))[0]:
                 worst[k] = (v, cname)
