@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(
     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum, float* running_mean,
     float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
     double* accum, unsigned* ticket) {
+  pdl_wait();
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_finalize_kernel(
     long long M, int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
     float* running_mean, float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale,
     float* shift, double* accum) {
+  pdl_wait();
   // 16 lanes per channel, one per accumulator replica (a serial loop over the replicas was a chain of L2 round
   // trips in a kernel that sits on the critical path between the convolution and the BN apply)
   static_assert(kReplicas == 16, "lane mapping below assumes 16 replicas");
@@ -255,10 +257,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_finalize_kernel(
   if (momentum >= 0.f && blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr && running_mean != nullptr)
     *num_batches_tracked += 1;
 }
-__global__ void bn_bump_kernel(long long* nbt) { *nbt += 1; }
+__global__ void bn_bump_kernel(long long* nbt) {
+  pdl_wait();
+  *nbt += 1;
+}
 
 __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv,
                                       float eps, float* scale, float* shift) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float istd = rsqrtf(rv[c] + eps);
@@ -274,6 +280,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
     const float* __restrict__ scale, const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
     const float* __restrict__ scale2, const float* __restrict__ shift2, int act, __nv_bfloat16* __restrict__ y,
     uint8_t* __restrict__ act_mask) {
+  pdl_wait();
   const int t = threadIdx.x;
   if (t >= rows_per_iter * cv) return;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ z, long long M, int C, int cv, int rows_per_iter, int act,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* __restrict__ partial) {
+  pdl_wait();
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -444,6 +452,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_final_kernel(const float* __restrict__ partial, int nblocks,
                                                                           int C, float* __restrict__ sums,
                                                                           float* dgamma_acc, float* dbeta_acc) {
+  pdl_wait();
   __shared__ double red[64][5];
   const int lane_o = threadIdx.x & 3, grp = threadIdx.x >> 2;
   const int o = blockIdx.x * 4 + lane_o;
@@ -481,6 +490,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz,
     __nv_bfloat16* __restrict__ g_out) {
+  pdl_wait();
   const int t = threadIdx.x;
   if (t >= rows_per_iter * cv) return;
   const int r0 = t / cv, v = t - r0 * cv;
@@ -581,7 +591,7 @@ extern "C" int b200_bn_stats(const void* z, long long M, int C, const float* gam
   B200_REQUIRE(z && mean && invstd && scale && shift && workspace && M > 0, B200_ERR_INVALID, "bn_stats: bad argument");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, B200_ERR_INVALID, "bn_stats: workspace misaligned");
   const RowMap rm = make_rowmap(C);
-  bn_stats_kernel<<<reduce_blocks(M, C, rm), kBnThreads, 0, (cudaStream_t)stream_>>>(
+  b200::launch(bn_stats_kernel, reduce_blocks(M, C, rm), kBnThreads, 0, (cudaStream_t)stream_,
       (const __nv_bfloat16*)z, M, C, rm.cv, rm.rows_per_iter, gamma, beta, eps, momentum, running_mean, running_var,
       nbt, mean, invstd, scale, shift, ws_accum(workspace), ws_ticket(workspace));
   B200_CHECK_LAUNCH("bn_stats_kernel");
@@ -596,11 +606,11 @@ extern "C" int b200_bn_finalize(long long M, int C, const float* gamma, const fl
   B200_REQUIRE(mean && invstd && scale && shift && workspace && M > 0, B200_ERR_INVALID, "bn_finalize: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   // NOTE: momentum < 0 reads *nbt before the bump below (same stream => ordered)
-  bn_finalize_kernel<<<(C + 15) / 16, kBnThreads, 0, stream>>>(
+  b200::launch(bn_finalize_kernel, (C + 15) / 16, kBnThreads, 0, stream,
       M, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd, scale, shift, ws_accum(workspace));
   B200_CHECK_LAUNCH("bn_finalize_kernel");
   if (momentum < 0.f && nbt != nullptr && running_mean != nullptr) {
-    bn_bump_kernel<<<1, 1, 0, stream>>>(nbt);
+    b200::launch(bn_bump_kernel, 1, 1, 0, stream, nbt);
     B200_CHECK_LAUNCH("bn_bump_kernel");
   }
   return B200_OK;
@@ -610,7 +620,7 @@ extern "C" int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta,
                                    const float* running_var, float eps, float* scale, float* shift,
                                    b200_stream_t stream_) {
   B200_REQUIRE(C > 0 && running_mean && running_var && scale && shift, B200_ERR_INVALID, "bn_eval_coeffs: bad argument");
-  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(C, gamma, beta, running_mean, running_var,
+  b200::launch(bn_eval_coeffs_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_, C, gamma, beta, running_mean, running_var,
                                                                          eps, scale, shift);
   B200_CHECK_LAUNCH("bn_eval_coeffs_kernel");
   return B200_OK;
@@ -630,13 +640,13 @@ extern "C" int b200_bn_apply(const void* z, long long M, int C, const float* sca
   const __nv_bfloat16* zz = (const __nv_bfloat16*)z;
   __nv_bfloat16* yy = (__nv_bfloat16*)y;
   if (residual)
-    bn_apply_kernel<1><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
+    b200::launch(bn_apply_kernel<1>, blocks, kBnThreads, 0, stream, zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
                                                          (const __nv_bfloat16*)residual, nullptr, nullptr, act, yy, act_mask);
   else if (z2)
-    bn_apply_kernel<2><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
+    b200::launch(bn_apply_kernel<2>, blocks, kBnThreads, 0, stream, zz, M, C, rm.cv, rm.rows_per_iter, scale, shift,
                                                          (const __nv_bfloat16*)z2, scale2, shift2, act, yy, act_mask);
   else
-    bn_apply_kernel<0><<<blocks, kBnThreads, 0, stream>>>(zz, M, C, rm.cv, rm.rows_per_iter, scale, shift, nullptr,
+    b200::launch(bn_apply_kernel<0>, blocks, kBnThreads, 0, stream, zz, M, C, rm.cv, rm.rows_per_iter, scale, shift, nullptr,
                                                          nullptr, nullptr, act, yy, act_mask);
   B200_CHECK_LAUNCH("bn_apply_kernel");
   return B200_OK;
@@ -660,11 +670,11 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* 
     const RowMap rm = make_rowmap_v<VEC>(C);                                                                   \
     blocks = partial_blocks(M, rm, MINB);                                                                      \
     if (src == 2)                                                                                              \
-      bn_bwd_reduce_kernel<VEC, ROWS, MINB, 2><<<blocks, kBnThreads, 0, stream>>>(B200_RED_ARGS(VEC));         \
+      b200::launch(bn_bwd_reduce_kernel<VEC, ROWS, MINB, 2>, blocks, kBnThreads, 0, stream, B200_RED_ARGS(VEC));         \
     else if (src == 1)                                                                                         \
-      bn_bwd_reduce_kernel<VEC, ROWS, MINB, 1><<<blocks, kBnThreads, 0, stream>>>(B200_RED_ARGS(VEC));         \
+      b200::launch(bn_bwd_reduce_kernel<VEC, ROWS, MINB, 1>, blocks, kBnThreads, 0, stream, B200_RED_ARGS(VEC));         \
     else                                                                                                       \
-      bn_bwd_reduce_kernel<VEC, ROWS, MINB, 0><<<blocks, kBnThreads, 0, stream>>>(B200_RED_ARGS(VEC));         \
+      b200::launch(bn_bwd_reduce_kernel<VEC, ROWS, MINB, 0>, blocks, kBnThreads, 0, stream, B200_RED_ARGS(VEC));         \
   } while (0)
   cudaStream_t stream = (cudaStream_t)stream_;
   float* partial = workspace + kAccumFloats;
@@ -682,7 +692,7 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* 
 #undef B200_LAUNCH_RED
 #undef B200_RED_ARGS
   B200_CHECK_LAUNCH("bn_bwd_reduce_kernel");
-  bn_bwd_reduce_final_kernel<<<(2 * C + 3) / 4, kBnThreads, 0, stream>>>(partial, blocks, C, sums, dgamma_acc,
+  b200::launch(bn_bwd_reduce_final_kernel, (2 * C + 3) / 4, kBnThreads, 0, stream, partial, blocks, C, sums, dgamma_acc,
                                                                            dbeta_acc);
   B200_CHECK_LAUNCH("bn_bwd_reduce_final_kernel");
   return B200_OK;
@@ -704,11 +714,11 @@ extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const uint8_t* act_
     const RowMap rm = make_rowmap_v<VEC>(C);                                                                 \
     const int blocks = stream_blocks(M, rm);                                                                 \
     if (src == 2)                                                                                            \
-      bn_bwd_dx_kernel<VEC, ROWS, MINB, 2><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(B200_DX_ARGS(VEC)); \
+      b200::launch(bn_bwd_dx_kernel<VEC, ROWS, MINB, 2>, blocks, kBnThreads, 0, (cudaStream_t)stream_, B200_DX_ARGS(VEC)); \
     else if (src == 1)                                                                                       \
-      bn_bwd_dx_kernel<VEC, ROWS, MINB, 1><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(B200_DX_ARGS(VEC)); \
+      b200::launch(bn_bwd_dx_kernel<VEC, ROWS, MINB, 1>, blocks, kBnThreads, 0, (cudaStream_t)stream_, B200_DX_ARGS(VEC)); \
     else                                                                                                     \
-      bn_bwd_dx_kernel<VEC, ROWS, MINB, 0><<<blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(B200_DX_ARGS(VEC)); \
+      b200::launch(bn_bwd_dx_kernel<VEC, ROWS, MINB, 0>, blocks, kBnThreads, 0, (cudaStream_t)stream_, B200_DX_ARGS(VEC)); \
   } while (0)
   if (C > 1024) {
     B200_LAUNCH_DX(8, 2, 3);

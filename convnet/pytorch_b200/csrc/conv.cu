@@ -175,6 +175,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // prologue above (barriers, TMEM, descriptor prefetch) overlaps the predecessor grid
   const uint32_t tmem_base = tmem_base_s;
 
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -501,6 +502,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // prologue above (barriers, TMEM, descriptor prefetch) overlaps the predecessor grid
   const uint32_t tmem_base = tmem_base_s;
 
   // work decomposition
@@ -700,6 +702,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
                                                                 int K_out, int taps, int C, int ckB, int c_chunks,
                                                                 int boxes_per_cta, int kt, int k_groups, int splits,
                                                                 int pitch) {
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int c4n = C >> 2;
   const long long total = static_cast<long long>(K_out) * taps * c4n;
@@ -928,7 +931,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (rc) return rc;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-  conv_igemm_kernel<<<grid, kIgemmThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  b200::launch(conv_igemm_kernel, grid, kIgemmThreads, smem_bytes, stream, tmA, tmB, tmC, tmR, p);
   B200_CHECK_LAUNCH("conv_igemm_kernel");
   return B200_OK;
 }
@@ -1180,13 +1183,13 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   rc = set_smem_attr((const void*)conv_wgrad_kernel, smem_bytes);
   if (rc) return rc;
   const int grid = tiles * p.splits;
-  conv_wgrad_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmDy, tmX, p);
+  b200::launch(conv_wgrad_kernel, grid, kThreads, smem_bytes, stream, tmDy, tmX, p);
   B200_CHECK_LAUNCH("conv_wgrad_kernel");
   if (p.partial != nullptr) {
     const long long total = static_cast<long long>(d->K) * p.taps_total * (Cw / 4);
     long long blocks = (total + 31) / 32;
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
-    conv_wgrad_reduce_kernel<<<static_cast<int>(blocks), 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, d->K, p.taps_total, Cw, p.ckB,
+    b200::launch(conv_wgrad_reduce_kernel, static_cast<int>(blocks), 32 * wgrad_reduce_warps(p.splits), 0, stream, p.partial, dw, d->K, p.taps_total, Cw, p.ckB,
                                                                           p.c_chunks, p.boxes_per_cta, p.kt, p.k_groups,
                                                                           p.splits, p.pitch);
     B200_CHECK_LAUNCH("conv_wgrad_reduce_kernel");

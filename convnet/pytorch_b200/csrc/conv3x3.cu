@@ -82,6 +82,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // prologue above (barriers, TMEM, descriptor prefetch) overlaps the predecessor grid
   const uint32_t tmem_base = tmem_base_s;
   // tile walk: dense -- tiles (m, n) round-robin over the CTAs; diagonal -- the CTA owns n-tile blockIdx.x % n_tiles and
   // walks the m-tiles with stride gridDim.x / n_tiles (the grid is a multiple of n_tiles)
@@ -431,9 +432,9 @@ int launch_halo(const void* src, const void* wmat, void* out, const void* res, c
     grid = per_n * p.n_tiles;
   }
   if (p.ntaps == 9)
-    conv_halo_kernel<9, 4><<<grid, kHThreads, smem_bytes, stream>>>(tmX, tmB, tmC, tmR, p);
+    b200::launch(conv_halo_kernel<9, 4>, grid, kHThreads, smem_bytes, stream, tmX, tmB, tmC, tmR, p);
   else
-    conv_halo_kernel<16, 1><<<grid, kHThreads, smem_bytes, stream>>>(tmX, tmB, tmC, tmR, p);
+    b200::launch(conv_halo_kernel<16, 1>, grid, kHThreads, smem_bytes, stream, tmX, tmB, tmC, tmR, p);
   B200_CHECK_LAUNCH("conv_halo_kernel");
   return B200_OK;
 }
@@ -501,6 +502,7 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // prologue above (barriers, TMEM, descriptor prefetch) overlaps the predecessor grid
   const uint32_t tmem_base = tmem_base_s;
 
   const int split = blockIdx.x / p.units;
@@ -586,6 +588,7 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_co
 __global__ void __launch_bounds__(256) conv_halo_wgrad_reduce_kernel(const float* __restrict__ partial,
                                                                      float* __restrict__ dw, int K_out, int ntaps, int C,
                                                                      int cw, int k_tiles, int splits, int ncols) {
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int c4n = C >> 2;
   const long long total = static_cast<long long>(K_out) * ntaps * c4n;
@@ -686,16 +689,16 @@ int launch_halo_wgrad(const void* x, const void* dy, float* dw, void* workspace,
   B200_REQUIRE(e == cudaSuccess, B200_ERR_CUDA, "conv halo wgrad: smem attribute (%d bytes): %s", smem_bytes,
                cudaGetErrorString(e));
   if (p.ntaps == 9)
-    conv_halo_wgrad_kernel<3, 3><<<p.units * p.splits, kWThreads, smem_bytes, stream>>>(tmDy, tmX, p);
+    b200::launch(conv_halo_wgrad_kernel<3, 3>, p.units * p.splits, kWThreads, smem_bytes, stream, tmDy, tmX, p);
   else
-    conv_halo_wgrad_kernel<4, 4><<<p.units * p.splits, kWThreads, smem_bytes, stream>>>(tmDy, tmX, p);
+    b200::launch(conv_halo_wgrad_kernel<4, 4>, p.units * p.splits, kWThreads, smem_bytes, stream, tmDy, tmX, p);
   B200_CHECK_LAUNCH("conv_halo_wgrad_kernel");
   const int Cw = window ? window : C;                 // row length of dw: [K][taps][Cw]
   const long long total = (long long)K_out * p.ntaps * (Cw / 4);
   long long blocks64 = (total + 31) / 32;
   if (blocks64 > 16LL * sm_count()) blocks64 = 16LL * sm_count();
   const int blocks = (int)blocks64;
-  conv_halo_wgrad_reduce_kernel<<<blocks, 32 * wgrad_reduce_warps(p.splits), 0, stream>>>(p.partial, dw, K_out, p.ntaps, Cw, p.cw, p.k_tiles, p.splits,
+  b200::launch(conv_halo_wgrad_reduce_kernel, blocks, 32 * wgrad_reduce_warps(p.splits), 0, stream, p.partial, dw, K_out, p.ntaps, Cw, p.cw, p.k_tiles, p.splits,
                                                             p.ncols);
   B200_CHECK_LAUNCH("conv_halo_wgrad_reduce_kernel");
   return B200_OK;

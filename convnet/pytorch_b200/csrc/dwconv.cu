@@ -23,6 +23,7 @@ __device__ __forceinline__ void dst8(__nv_bfloat16* p, const float (&f)[8]) {
 __global__ void __launch_bounds__(256) dw_fprop_kernel(const __nv_bfloat16* __restrict__ x,
                                                        const __nv_bfloat16* __restrict__ w, b200_conv_desc d,
                                                        __nv_bfloat16* __restrict__ y) {
+  pdl_wait();
   const int cv = d.C >> 3;
   const long long total = (long long)d.N * d.P * d.Q * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256) dw_fprop_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) dw_dgrad_kernel(const __nv_bfloat16* __restrict__ dy,
                                                        const __nv_bfloat16* __restrict__ w, b200_conv_desc d,
                                                        __nv_bfloat16* __restrict__ dx) {
+  pdl_wait();
   const int cv = d.C >> 3;
   const long long total = (long long)d.N * d.H * d.W * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_wgrad_partial_kernel(const __nv
                                                                       const __nv_bfloat16* __restrict__ dy,
                                                                       b200_conv_desc d, int cv, int rows_per_iter,
                                                                       float* __restrict__ partial) {
+  pdl_wait();
   __shared__ float red[kDwThreads][9];
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(kDwThreads) dw_wgrad_partial_kernel(const __nv
 }
 
 __global__ void dw_wgrad_final_kernel(const float* __restrict__ partial, int nblocks, int n, float* __restrict__ dw) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
@@ -179,7 +183,7 @@ extern "C" int b200_dwconv_fprop(const b200_conv_desc* d, const void* x, const v
   if (rc) return rc;
   B200_REQUIRE(x && w && y, B200_ERR_INVALID, "dwconv_fprop: null pointer");
   const long long total = (long long)d->N * d->P * d->Q * (d->C / 8);
-  dw_fprop_kernel<<<dw_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+  b200::launch(dw_fprop_kernel, dw_grid(total), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
                                                                   *d, (__nv_bfloat16*)y);
   B200_CHECK_LAUNCH("dw_fprop_kernel");
   return B200_OK;
@@ -191,7 +195,7 @@ extern "C" int b200_dwconv_dgrad(const b200_conv_desc* d, const void* dy, const 
   if (rc) return rc;
   B200_REQUIRE(dy && w && dx, B200_ERR_INVALID, "dwconv_dgrad: null pointer");
   const long long total = (long long)d->N * d->H * d->W * (d->C / 8);
-  dw_dgrad_kernel<<<dw_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w,
+  b200::launch(dw_dgrad_kernel, dw_grid(total), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w,
                                                                   *d, (__nv_bfloat16*)dx);
   B200_CHECK_LAUNCH("dw_dgrad_kernel");
   return B200_OK;
@@ -211,10 +215,10 @@ extern "C" int b200_dwconv_wgrad(const b200_conv_desc* d, const void* x, const v
   const int n = d->R * d->S * d->C;
   B200_REQUIRE(workspace_bytes >= (size_t)blocks * n * sizeof(float), B200_ERR_INVALID,
                "dwconv_wgrad: workspace too small (%zu < %zu)", workspace_bytes, (size_t)blocks * n * sizeof(float));
-  dw_wgrad_partial_kernel<<<(int)blocks, kDwThreads, 0, (cudaStream_t)stream>>>(
+  b200::launch(dw_wgrad_partial_kernel, (int)blocks, kDwThreads, 0, (cudaStream_t)stream,
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, *d, cv, rows_per_iter, workspace);
   B200_CHECK_LAUNCH("dw_wgrad_partial_kernel");
-  dw_wgrad_final_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, (int)blocks, n, dw);
+  b200::launch(dw_wgrad_final_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, workspace, (int)blocks, n, dw);
   B200_CHECK_LAUNCH("dw_wgrad_final_kernel");
   return B200_OK;
 }

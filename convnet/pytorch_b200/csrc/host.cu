@@ -49,6 +49,11 @@ EncodeIm2colFn encode_im2col_fn() {
   return fn;
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("B200_PDL") ? atoi(getenv("B200_PDL")) != 0 : false;
+  return on;
+}
+
 int wgrad_reduce_warps(int splits) {
   static const int env = getenv("B200_WGRAD_REDUCE_WARPS") ? atoi(getenv("B200_WGRAD_REDUCE_WARPS")) : 0;
   int w = env > 0 ? env : 8;

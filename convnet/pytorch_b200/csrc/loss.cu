@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __r
                                                                 const float* __restrict__ grad_scale_dev,
                                                                 float* __restrict__ row_loss,
                                                                 __nv_bfloat16* __restrict__ dlogits) {
+  pdl_wait();
   // row_loss layout: [0, B) per-sample loss, [B, 2B) number of classes scoring strictly above the target class
   // (rank of the target: top-1 <=> 0, top-5 <=> < 5 -- utils/meters.py:59-72 of the reference, ties aside)
   __shared__ float sh[kCeThreads / 32];
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __r
 // order (bit-reproducible, no atomics, no pre-zeroed output)
 __global__ void __launch_bounds__(kCeThreads) ce_mean_kernel(const float* __restrict__ row_loss, int B,
                                                              float* __restrict__ loss) {
+  pdl_wait();
   __shared__ float sh[kCeThreads / 32];
   float s = 0.f, t1 = 0.f, t5 = 0.f;
   for (int b = threadIdx.x; b < B; b += kCeThreads) {
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(kCeThreads) ce_mean_kernel(const float* __rest
 
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ m, int B, int K,
                                                           float* __restrict__ out) {
+  pdl_wait();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   float s = 0.f;
@@ -118,11 +121,11 @@ extern "C" int b200_softmax_ce(const float* logits, const long long* target, int
   B200_REQUIRE((loss == nullptr) == (row_loss == nullptr), B200_ERR_INVALID,
                "softmax_ce: loss and row_loss must be given together");
   B200_REQUIRE(loss != nullptr || dlogits_bf16 != nullptr, B200_ERR_INVALID, "softmax_ce: nothing to compute");
-  softmax_ce_kernel<<<B, kCeThreads, 0, (cudaStream_t)stream>>>(logits, target, B, classes, ld, smooth_eps, grad_scale,
+  b200::launch(softmax_ce_kernel, B, kCeThreads, 0, (cudaStream_t)stream, logits, target, B, classes, ld, smooth_eps, grad_scale,
                                                               grad_scale_dev, row_loss, (__nv_bfloat16*)dlogits_bf16);
   B200_CHECK_LAUNCH("softmax_ce_kernel");
   if (loss != nullptr) {
-    ce_mean_kernel<<<1, kCeThreads, 0, (cudaStream_t)stream>>>(row_loss, B, loss);
+    b200::launch(ce_mean_kernel, 1, kCeThreads, 0, (cudaStream_t)stream, row_loss, B, loss);
     B200_CHECK_LAUNCH("ce_mean_kernel");
   }
   return B200_OK;
@@ -130,7 +133,7 @@ extern "C" int b200_softmax_ce(const float* logits, const long long* target, int
 
 extern "C" int b200_colsum_bf16(const void* m, int B, int K, float* out, b200_stream_t stream) {
   B200_REQUIRE(m && out && B > 0 && K > 0, B200_ERR_INVALID, "colsum_bf16: bad argument");
-  colsum_bf16_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)m, B, K, out);
+  b200::launch(colsum_bf16_kernel, (K + 255) / 256, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)m, B, K, out);
   B200_CHECK_LAUNCH("colsum_bf16_kernel");
   return B200_OK;
 }

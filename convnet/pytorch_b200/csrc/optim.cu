@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) fused_sgd_kernel(float* __restrict__ p32,
                                                         float dampening, float wd, float inv_scale,
                                                         const float* __restrict__ clip_coef, int first_step,
                                                         int zero_grad) {
+  pdl_wait();
   const float gs = inv_scale * (clip_coef != nullptr ? __ldg(clip_coef) : 1.f);
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) fused_sgd_kernel(float* __restrict__ p32,
 constexpr int kSumsqBlocks = 592;
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n,
                                                             float* __restrict__ partial) {
+  pdl_wait();
   __shared__ float sh[8];
   float acc = 0.f;
   const long long n4 = n >> 2;
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   }
 }
 __global__ void sumsq_final_kernel(const float* __restrict__ partial, int nb, float* out) {
+  pdl_wait();
   __shared__ double sh[8];
   double acc = 0.0;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += (double)partial[i];
@@ -103,6 +106,7 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, int nb, fl
 
 __global__ void grad_coef_kernel(const float* sumsq, float inv_scale, int mode, float max_norm, float momentum,
                                  float* state, float* coef_out, float* norm_out) {
+  pdl_wait();
   const float norm = sqrtf(*sumsq) * inv_scale;
   float coef = 1.f;
   if (mode == 0) {
@@ -134,7 +138,7 @@ extern "C" int b200_fused_sgd(float* p32, float* g32, float* m32, void* p16, lon
   long long blocks = ((n + 3) / 4 + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  fused_sgd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p32, g32, m32, (__nv_bfloat16*)p16, n, wd_count, lr,
+  b200::launch(fused_sgd_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, p32, g32, m32, (__nv_bfloat16*)p16, n, wd_count, lr,
                                                                  momentum, dampening, weight_decay, inv_scale,
                                                                  clip_coef_dev, first_step, zero_grad);
   B200_CHECK_LAUNCH("fused_sgd_kernel");
@@ -145,9 +149,9 @@ extern "C" int b200_sumsq(const float* g, long long n, float* out, float* worksp
   B200_REQUIRE(g && out && workspace && n > 0, B200_ERR_INVALID, "sumsq: bad argument");
   long long blocks = ((n + 3) / 4 + 255) / 256;
   if (blocks > kSumsqBlocks) blocks = kSumsqBlocks;
-  sumsq_partial_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, workspace);
+  b200::launch(sumsq_partial_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, g, n, workspace);
   B200_CHECK_LAUNCH("sumsq_partial_kernel");
-  sumsq_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, (int)blocks, out);
+  b200::launch(sumsq_final_kernel, 1, 256, 0, (cudaStream_t)stream, workspace, (int)blocks, out);
   B200_CHECK_LAUNCH("sumsq_final_kernel");
   return B200_OK;
 }
@@ -155,7 +159,7 @@ extern "C" int b200_sumsq(const float* g, long long n, float* out, float* worksp
 extern "C" int b200_grad_coef(const float* sumsq, float inv_scale, int mode, float max_norm, float momentum,
                               float* state, float* coef_out, float* norm_out, b200_stream_t stream) {
   B200_REQUIRE(sumsq && coef_out && (mode == 0 || state), B200_ERR_INVALID, "grad_coef: bad argument");
-  grad_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, inv_scale, mode, max_norm, momentum, state, coef_out,
+  b200::launch(grad_coef_kernel, 1, 1, 0, (cudaStream_t)stream, sumsq, inv_scale, mode, max_norm, momentum, state, coef_out,
                                                      norm_out);
   B200_CHECK_LAUNCH("grad_coef_kernel");
   return B200_OK;

@@ -23,6 +23,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W,
                                                           int C, int OH, int OW, __nv_bfloat16* __restrict__ y,
                                                           uint8_t* __restrict__ amax) {
+  pdl_wait();
   const int cv = C >> 3;
   const long long total = (long long)N * OH * OW * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* _
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                           const uint8_t* __restrict__ amax, int N, int H, int W, int C,
                                                           int OH, int OW, __nv_bfloat16* __restrict__ dx) {
+  pdl_wait();
   const int cv = C >> 3;
   const long long total = (long long)N * H * W * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
 
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int HW, int C,
                                                           __nv_bfloat16* __restrict__ y) {
+  pdl_wait();
   const int cv = C >> 3;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * cv) return;
@@ -137,6 +140,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* _
 
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int N, int HW, int C,
                                                           __nv_bfloat16* __restrict__ dx) {
+  pdl_wait();
   const int cv = C >> 3;
   const long long total = (long long)N * HW * cv;
   const float inv = 1.f / (float)HW;
@@ -171,7 +175,7 @@ extern "C" int b200_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, 
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "maxpool_fwd: C=%d must be a multiple of 8", C);
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * OH * OW * (C / 8);
-  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, OH,
+  b200::launch(maxpool_fwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, N, H, W, C, OH,
                                                                            OW, (__nv_bfloat16*)y, argmax);
   B200_CHECK_LAUNCH("maxpool_fwd_kernel");
   return B200_OK;
@@ -183,7 +187,7 @@ extern "C" int b200_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, int 
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "maxpool_bwd: C=%d must be a multiple of 8", C);
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, argmax, N, H, W,
+  b200::launch(maxpool_bwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, argmax, N, H, W,
                                                                            C, OH, OW, (__nv_bfloat16*)dx);
   B200_CHECK_LAUNCH("maxpool_bwd_kernel");
   return B200_OK;
@@ -193,7 +197,7 @@ extern "C" int b200_avgpool_fwd(const void* x, int N, int HW, int C, void* y, b2
   B200_REQUIRE(x && y && N > 0 && HW > 0, B200_ERR_INVALID, "avgpool_fwd: bad argument");
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "avgpool_fwd: C=%d must be a multiple of 8", C);
   const int total = N * (C / 8);
-  avgpool_fwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, HW, C,
+  b200::launch(avgpool_fwd_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, N, HW, C,
                                                                           (__nv_bfloat16*)y);
   B200_CHECK_LAUNCH("avgpool_fwd_kernel");
   return B200_OK;
@@ -203,7 +207,7 @@ extern "C" int b200_avgpool_bwd(const void* dy, int N, int HW, int C, void* dx, 
   B200_REQUIRE(dy && dx && N > 0 && HW > 0, B200_ERR_INVALID, "avgpool_bwd: bad argument");
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "avgpool_bwd: C=%d must be a multiple of 8", C);
   const long long total = (long long)N * HW * (C / 8);
-  avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, N, HW, C,
+  b200::launch(avgpool_bwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, N, HW, C,
                                                                            (__nv_bfloat16*)dx);
   B200_CHECK_LAUNCH("avgpool_bwd_kernel");
   return B200_OK;

@@ -10,6 +10,7 @@ namespace b200 {
 
 __global__ void __launch_bounds__(256) input_prep_kernel(const float* __restrict__ x, int N, int C, int H, int W,
                                                          int Cpad, int mode, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
   // one thread per output pixel; Cpad is a multiple of 8
   const int brd = mode == 2 ? 2 : 0;                       // low border of the padded space-to-depth layout
   const int OH = mode == 0 ? H : H / 2 + (mode == 2 ? 3 : 0), OW = mode == 0 ? W : W / 2 + (mode == 2 ? 3 : 0);
@@ -55,6 +56,7 @@ struct U8Norm { float scale[4], bias[4]; };
 __global__ void __launch_bounds__(256) input_prep_u8_kernel(const uint8_t* __restrict__ x, int N, int C, int H, int W,
                                                             int Cpad, int mode, U8Norm nm,
                                                             __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
   const int brd = mode == 2 ? 2 : 0;
   const int OH = mode == 0 ? H : H / 2 + (mode == 2 ? 3 : 0), OW = mode == 0 ? W : W / 2 + (mode == 2 ? 3 : 0);
   const long long total = (long long)N * OH * OW;
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) input_prep_u8_kernel(const uint8_t* __res
 // bf16 [K][T][C] -> [C][T][K]; one 32x32 tile per block, blockIdx.z = tap
 __global__ void __launch_bounds__(256) weight_transpose_kernel(const __nv_bfloat16* __restrict__ src,
                                                                __nv_bfloat16* __restrict__ dst, int K, int T, int C) {
+  pdl_wait();
   __shared__ __nv_bfloat16 tile[32][33];
   const int t = blockIdx.z;
   const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(256) weight_transpose_kernel(const __nv_bfloat
 __global__ void __launch_bounds__(256) weight_transpose_batched_kernel(const __nv_bfloat16* __restrict__ src_base,
                                                                        __nv_bfloat16* __restrict__ dst_base,
                                                                        const int* __restrict__ jobs, int njobs) {
+  pdl_wait();
   __shared__ __nv_bfloat16 tile[32][33];
   int lo = 0, hi = njobs - 1;
   const int g = blockIdx.x;
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(256) weight_transpose_batched_kernel(const __n
 // r = 2*ah + bh - 1, s = 2*aw + bw - 1 (out-of-range -> 0)
 __global__ void stem_w_to_s2d_kernel(const float* __restrict__ w, int K, int C, int Cpad,
                                      __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
   const int total = K * 16 * Cpad;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int ch = idx % Cpad;
@@ -165,6 +170,7 @@ __global__ void stem_w_to_s2d_kernel(const float* __restrict__ w, int K, int C, 
 // reverse gather for the gradient: dw[K][7][7][C] += dw_s2d[K][16][Cpad]
 __global__ void stem_wgrad_from_s2d_kernel(const float* __restrict__ dws, int K, int C, int Cpad,
                                            float* __restrict__ dw) {
+  pdl_wait();
   const int total = K * 49 * C;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int c = idx % C;
@@ -178,6 +184,7 @@ __global__ void stem_wgrad_from_s2d_kernel(const float* __restrict__ dws, int K,
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src,
                                                             __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_wait();
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -216,7 +223,7 @@ extern "C" int b200_input_prep(const float* x, int N, int C, int H, int W, int C
     B200_REQUIRE(false, B200_ERR_INVALID, "input_prep: unknown mode %d", mode);
   }
   const long long total = (long long)N * (mode == 0 ? (long long)H * W : (long long)(H / 2 + (mode == 2 ? 3 : 0)) * (W / 2 + (mode == 2 ? 3 : 0)));
-  input_prep_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(x, N, C, H, W, Cpad, mode,
+  b200::launch(input_prep_kernel, grid_cap(total, 256), 256, 0, (cudaStream_t)stream, x, N, C, H, W, Cpad, mode,
                                                                           (__nv_bfloat16*)out);
   B200_CHECK_LAUNCH("input_prep_kernel");
   return B200_OK;
@@ -238,7 +245,7 @@ extern "C" int b200_input_prep_u8(const uint8_t* x_nhwc, int N, int C, int H, in
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  input_prep_u8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x_nhwc, N, C, H, W, Cpad, mode, nm,
+  b200::launch(input_prep_u8_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, x_nhwc, N, C, H, W, Cpad, mode, nm,
                                                                        (__nv_bfloat16*)out);
   B200_CHECK_LAUNCH("input_prep_u8_kernel");
   return B200_OK;
@@ -247,7 +254,7 @@ extern "C" int b200_input_prep_u8(const uint8_t* x_nhwc, int N, int C, int H, in
 extern "C" int b200_weight_transpose(const void* src, void* dst, int K, int T, int C, b200_stream_t stream) {
   B200_REQUIRE(src && dst && K > 0 && T > 0 && C > 0, B200_ERR_INVALID, "weight_transpose: bad argument");
   dim3 grid((C + 31) / 32, (K + 31) / 32, T);
-  weight_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, K, T,
+  b200::launch(weight_transpose_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, K, T,
                                                                 C);
   B200_CHECK_LAUNCH("weight_transpose_kernel");
   return B200_OK;
@@ -257,7 +264,7 @@ extern "C" int b200_weight_transpose_batched(const void* src_base, void* dst_bas
                                              int total_tiles, b200_stream_t stream) {
   B200_REQUIRE(src_base && dst_base && jobs && njobs > 0 && total_tiles > 0, B200_ERR_INVALID,
                "weight_transpose_batched: bad argument");
-  weight_transpose_batched_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(
+  b200::launch(weight_transpose_batched_kernel, total_tiles, 256, 0, (cudaStream_t)stream,
       (const __nv_bfloat16*)src_base, (__nv_bfloat16*)dst_base, jobs, njobs);
   B200_CHECK_LAUNCH("weight_transpose_batched_kernel");
   return B200_OK;
@@ -265,7 +272,7 @@ extern "C" int b200_weight_transpose_batched(const void* src_base, void* dst_bas
 
 extern "C" int b200_stem_weight_to_s2d(const float* w, int K, int C, int Cpad, void* w_s2d, b200_stream_t stream) {
   B200_REQUIRE(w && w_s2d && K > 0 && C > 0 && Cpad >= 4 * C, B200_ERR_INVALID, "stem_weight_to_s2d: bad argument");
-  stem_w_to_s2d_kernel<<<(K * 16 * Cpad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, K, C, Cpad,
+  b200::launch(stem_w_to_s2d_kernel, (K * 16 * Cpad + 255) / 256, 256, 0, (cudaStream_t)stream, w, K, C, Cpad,
                                                                                     (__nv_bfloat16*)w_s2d);
   B200_CHECK_LAUNCH("stem_w_to_s2d_kernel");
   return B200_OK;
@@ -273,7 +280,7 @@ extern "C" int b200_stem_weight_to_s2d(const float* w, int K, int C, int Cpad, v
 
 extern "C" int b200_stem_wgrad_from_s2d(const float* dw_s2d, int K, int C, int Cpad, float* dw, b200_stream_t stream) {
   B200_REQUIRE(dw_s2d && dw && K > 0 && C > 0 && Cpad >= 4 * C, B200_ERR_INVALID, "stem_wgrad_from_s2d: bad argument");
-  stem_wgrad_from_s2d_kernel<<<(K * 49 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dw_s2d, K, C, Cpad, dw);
+  b200::launch(stem_wgrad_from_s2d_kernel, (K * 49 * C + 255) / 256, 256, 0, (cudaStream_t)stream, dw_s2d, K, C, Cpad, dw);
   B200_CHECK_LAUNCH("stem_wgrad_from_s2d_kernel");
   return B200_OK;
 }
@@ -281,7 +288,7 @@ extern "C" int b200_stem_wgrad_from_s2d(const float* dw_s2d, int K, int C, int C
 extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, b200_stream_t stream) {
   B200_REQUIRE(src && dst && n >= 0, B200_ERR_INVALID, "cast_f32_to_bf16: bad argument");
   if (n == 0) return B200_OK;
-  cast_f32_bf16_kernel<<<grid_cap((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  b200::launch(cast_f32_bf16_kernel, grid_cap((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, n);
   B200_CHECK_LAUNCH("cast_f32_bf16_kernel");
   return B200_OK;
 }
@@ -299,6 +306,7 @@ extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, b
 namespace b200 {
 __global__ void __launch_bounds__(256) group_pack_kernel(const float* __restrict__ wg, int K, int T, int C, int groups,
                                                          int Wd, int transpose, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
   const int cg = C / groups, kg = K / groups;
   const int rows = transpose ? C : K;
   const long long total = (long long)rows * T * Wd;
@@ -319,6 +327,7 @@ __global__ void __launch_bounds__(256) group_pack_kernel(const float* __restrict
 }
 __global__ void __launch_bounds__(256) group_unpack_kernel(const float* __restrict__ dw_win, int K, int T, int C,
                                                            int groups, int Wd, float* __restrict__ dwg) {
+  pdl_wait();
   const int cg = C / groups, kg = K / groups;
   const long long total = (long long)K * T * cg;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -340,7 +349,7 @@ extern "C" int b200_group_weight_pack(const float* w_grouped, int K, int T, int 
                B200_ERR_UNSUPPORTED, "group_weight_pack: window %d must be a multiple of the group width and divide C == K",
                window);
   const long long total = (long long)(transpose ? C : K) * T * window;
-  b200::group_pack_kernel<<<b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  b200::launch(b200::group_pack_kernel, b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream,
       w_grouped, K, T, C, groups, window, transpose, (__nv_bfloat16*)out_bf16);
   B200_CHECK_LAUNCH("group_pack_kernel");
   return B200_OK;
@@ -352,7 +361,7 @@ extern "C" int b200_group_wgrad_unpack(const float* dw_win, int K, int T, int C,
                    window > 0 && window % (C / groups) == 0,
                B200_ERR_INVALID, "group_wgrad_unpack: bad argument");
   const long long total = (long long)K * T * (C / groups);
-  b200::group_unpack_kernel<<<b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_win, K, T, C, groups, window,
+  b200::launch(b200::group_unpack_kernel, b200::grid_cap(total, 256), 256, 0, (cudaStream_t)stream, dw_win, K, T, C, groups, window,
                                                                                        dw_grouped);
   B200_CHECK_LAUNCH("group_unpack_kernel");
   return B200_OK;

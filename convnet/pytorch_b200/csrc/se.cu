@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ b,
                                                         const float* __restrict__ logit, int HW, int C,
                                                         __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
   __shared__ float red[32][65];
   const int n = blockIdx.x, slab = blockIdx.y;
   const int v = threadIdx.x & 7, lane = threadIdx.x >> 3;      // 8 vectors of 8 channels, 32 row lanes
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) se_scale_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ logit,
                                                        const __nv_bfloat16* __restrict__ dmean, long long total_vec,
                                                        int HW, int C, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
   const int cv = C >> 3;
   const float inv = 1.f / (float)HW;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(256) se_scale_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                       const __nv_bfloat16* __restrict__ y, long long nvec, int act,
                                                       __nv_bfloat16* __restrict__ dx) {
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float g[8], f[8];
     se_ld8(dy + i * 8, g);
@@ -144,7 +147,7 @@ extern "C" int b200_se_pool(const void* r, int N, int HW, int C, void* mean_bf16
   B200_REQUIRE(r && mean_bf16, B200_ERR_INVALID, "se_pool: null pointer");
   SE_CHECK_SHAPE("se_pool");
   dim3 grid(N, (C + 63) / 64);
-  se_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)r, nullptr, nullptr, HW, C,
+  b200::launch(se_reduce_kernel<0>, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)r, nullptr, nullptr, HW, C,
                                                              (__nv_bfloat16*)mean_bf16);
   B200_CHECK_LAUNCH("se_reduce_kernel<0>");
   return B200_OK;
@@ -154,7 +157,7 @@ extern "C" int b200_se_scale_fwd(const void* r, const float* logit, int N, int H
   B200_REQUIRE(r && logit && out, B200_ERR_INVALID, "se_scale_fwd: null pointer");
   SE_CHECK_SHAPE("se_scale_fwd");
   const long long total = (long long)N * HW * (C / 8);
-  se_scale_kernel<0><<<se_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)r, logit, nullptr, total,
+  b200::launch(se_scale_kernel<0>, se_grid(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)r, logit, nullptr, total,
                                                                            HW, C, (__nv_bfloat16*)out);
   B200_CHECK_LAUNCH("se_scale_kernel<0>");
   return B200_OK;
@@ -165,7 +168,7 @@ extern "C" int b200_se_bwd_reduce(const void* g, const void* r, const float* log
   B200_REQUIRE(g && r && logit && dlogit_bf16, B200_ERR_INVALID, "se_bwd_reduce: null pointer");
   SE_CHECK_SHAPE("se_bwd_reduce");
   dim3 grid(N, (C + 63) / 64);
-  se_reduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)r, logit, HW,
+  b200::launch(se_reduce_kernel<1>, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)g, (const __nv_bfloat16*)r, logit, HW,
                                                              C, (__nv_bfloat16*)dlogit_bf16);
   B200_CHECK_LAUNCH("se_reduce_kernel<1>");
   return B200_OK;
@@ -176,7 +179,7 @@ extern "C" int b200_se_bwd_dx(const void* g, const float* logit, const void* dme
   B200_REQUIRE(g && logit && dmean_bf16 && dr, B200_ERR_INVALID, "se_bwd_dx: null pointer");
   SE_CHECK_SHAPE("se_bwd_dx");
   const long long total = (long long)N * HW * (C / 8);
-  se_scale_kernel<1><<<se_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, logit,
+  b200::launch(se_scale_kernel<1>, se_grid(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)g, logit,
                                                                            (const __nv_bfloat16*)dmean_bf16, total, HW, C,
                                                                            (__nv_bfloat16*)dr);
   B200_CHECK_LAUNCH("se_scale_kernel<1>");
@@ -185,7 +188,7 @@ extern "C" int b200_se_bwd_dx(const void* g, const float* logit, const void* dme
 
 extern "C" int b200_act_bwd(const void* dy, const void* y, long long n, int act, void* dx, b200_stream_t stream) {
   B200_REQUIRE(dy && y && dx && n > 0 && n % 8 == 0, B200_ERR_INVALID, "act_bwd: bad argument (n %% 8 == 0 needed)");
-  act_bwd_kernel<<<se_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+  b200::launch(act_bwd_kernel, se_grid(n / 8, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
                                                                        n / 8, act, (__nv_bfloat16*)dx);
   B200_CHECK_LAUNCH("act_bwd_kernel");
   return B200_OK;
