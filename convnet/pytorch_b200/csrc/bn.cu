@@ -361,13 +361,67 @@ __device__ __forceinline__ void loadfv(const float* p, float (&f)[VEC]) {
   }
 }
 
+// Gradient arriving at a pre-pool pixel of a 3x3 / stride 2 / pad 1 max pool, gathered from the POOLED gradient dp
+// [N, OH, OW, C] through the argmax bytes (pool.cu) -- the stem's BN backward reads dp + one byte per pooled element
+// instead of a materialised [N, H, W, C] gradient tensor (saves the max-pool backward kernel: one write and two reads
+// of the largest activation of the network).  A pixel lies in at most 2 x 2 windows; fp32 sum, no rounding.
+struct PoolGeom {
+  int H, W, OH, OW;
+};
+template <int VEC>
+__device__ __forceinline__ void pool_gather(const __nv_bfloat16* __restrict__ dp, const uint8_t* __restrict__ amax,
+                                            long long row, long long col, int C, const PoolGeom& pg, float (&g)[VEC]) {
+  const int w = (int)(row % pg.W);
+  const long long t = row / pg.W;
+  const int h = (int)(t % pg.H);
+  const long long n = t / pg.H;
+  const int p_lo = h >> 1, q_lo = w >> 1;
+  uint32_t ab[4][VEC / 4];
+  uint32_t gr[4][VEC / 2];
+  int want[4];
+  bool ok[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = p_lo + (j >> 1), q = q_lo + (j & 1);
+    ok[j] = p <= ((h + 1) >> 1) && q <= ((w + 1) >> 1) && p < pg.OH && q < pg.OW;
+    want[j] = (h - (2 * p - 1)) * 3 + (w - (2 * q - 1));
+    if (ok[j]) {
+      const long long o = ((n * pg.OH + p) * pg.OW + q) * C + col;
+      if constexpr (VEC == 8) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(amax + o));
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(dp + o));
+        ab[j][0] = a.x; ab[j][1] = a.y;
+        gr[j][0] = d.x; gr[j][1] = d.y; gr[j][2] = d.z; gr[j][3] = d.w;
+      } else {
+        ab[j][0] = __ldg(reinterpret_cast<const uint32_t*>(amax + o));
+        const uint2 d = __ldg(reinterpret_cast<const uint2*>(dp + o));
+        gr[j][0] = d.x; gr[j][1] = d.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) g[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!ok[j]) continue;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int b = (ab[j][i >> 2] >> (8 * (i & 3))) & 0xff;
+      const float2 g2 = unpack_bf16x2(gr[j][i >> 1]);
+      if (b == want[j]) g[i] += (i & 1) ? g2.y : g2.x;
+    }
+  }
+}
+
 // ---- backward reduce: dbeta = sum g, dgamma = sum g * xhat ------------------------------------------
-template <int VEC, int ROWS, int MINB, int SRC>   // SRC: activation argument 0 recomputed from z, 1 = y, 2 = mask bits
+// SRC: activation argument 0 recomputed from z, 1 = y, 2 = mask bits; 3 = like 0, with the gradient gathered from a
+// max-pooled gradient (dy = dp, amask = argmax bytes, pool_gather above)
+template <int VEC, int ROWS, int MINB, int SRC>
 __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const uint8_t* __restrict__ amask,
     const __nv_bfloat16* __restrict__ z, long long M, int C, int cv, int rows_per_iter, int act,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float* __restrict__ partial) {
+    const float* __restrict__ beta, float* __restrict__ partial, const PoolGeom pg) {
   pdl_wait();
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
@@ -381,7 +435,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
   if (active) {
     float mu[VEC], sc[VEC], sh[VEC];
     loadfv<VEC>(mean + v * VEC, mu);
-    if (SRC == 0 && act != B200_ACT_NONE) {
+    if ((SRC == 0 || SRC == 3) && act != B200_ACT_NONE) {
       float is[VEC];
       loadfv<VEC>(invstd + v * VEC, is);
       if (gamma) loadfv<VEC>(gamma + v * VEC, sc);
@@ -402,7 +456,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
         const long long rr = r + (long long)u * rows_per_iter;
         ok[u] = rr < row_end;
         if (ok[u]) {
-          rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
+          if (SRC != 3) rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
           rz[u] = ldv(z + rr * C + col, (RawVec<VEC>*)nullptr);
           if (SRC == 1) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
           if (SRC == 2) rm[u] = static_cast<uint32_t>(__ldg(amask + ((rr * C + col) >> 3))) >> (col & 7 & ~(VEC - 1));
@@ -412,7 +466,8 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
       for (int u = 0; u < ROWS; ++u) {
         if (!ok[u]) continue;
         float da[VEC], za[VEC], ya[VEC];
-        unpackv(rd[u], da);
+        if (SRC == 3) pool_gather<VEC>(dy, amask, r + (long long)u * rows_per_iter, col, C, pg, da);
+        else unpackv(rd[u], da);
         unpackv(rz[u], za);
         if (SRC == 1) unpackv(ry[u], ya);
 #pragma unroll
@@ -483,13 +538,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_final_kernel(const f
 }
 
 // ---- backward dx --------------------------------------------------------------------------------
-template <int VEC, int ROWS, int MINB, int SRC>   // SRC: activation argument 0 recomputed from z, 1 = y, 2 = mask bits
+template <int VEC, int ROWS, int MINB, int SRC>   // SRC as in bn_bwd_reduce_kernel
 __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const uint8_t* __restrict__ amask,
     const __nv_bfloat16* __restrict__ z, long long M, int C, int cv, int rows_per_iter, int act,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz,
-    __nv_bfloat16* __restrict__ g_out) {
+    __nv_bfloat16* __restrict__ g_out, const PoolGeom pg) {
   pdl_wait();
   const int t = threadIdx.x;
   if (t >= rows_per_iter * cv) return;
@@ -528,7 +583,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
       const long long rr = r + (long long)u * rows_per_iter;
       ok[u] = rr < row_end;
       if (ok[u]) {
-        rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
+        if (SRC != 3) rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
         rz[u] = ldv(z + rr * C + col, (RawVec<VEC>*)nullptr);
         if (SRC == 1) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
         if (SRC == 2) rm[u] = static_cast<uint32_t>(__ldg(amask + ((rr * C + col) >> 3))) >> (col & 7 & ~(VEC - 1));
@@ -539,7 +594,8 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
       if (!ok[u]) continue;
       const long long rr = r + (long long)u * rows_per_iter;
       float da[VEC], za[VEC], ya[VEC];
-      unpackv(rd[u], da);
+      if (SRC == 3) pool_gather<VEC>(dy, amask, rr, col, C, pg, da);
+      else unpackv(rd[u], da);
       unpackv(rz[u], za);
       if (SRC == 1) unpackv(ry[u], ya);
 #pragma unroll
@@ -652,24 +708,26 @@ extern "C" int b200_bn_apply(const void* z, long long M, int C, const float* sca
   return B200_OK;
 }
 
-extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M,
-                                  int C, int act,
-                                  const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                  float* sums, float* dgamma_acc, float* dbeta_acc, float* workspace,
-                                  b200_stream_t stream_) {
+// pooled: dy is the gradient of a 3x3/s2/p1 max pool's OUTPUT and act_mask holds the argmax bytes (SRC 3)
+static int bn_bwd_reduce_impl(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M, int C,
+                              int act, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                              float* sums, float* dgamma_acc, float* dbeta_acc, float* workspace, b200_stream_t stream_,
+                              bool pooled, const PoolGeom pg) {
   int rc = check_c(C, "bn_bwd_reduce");
   if (rc) return rc;
   B200_REQUIRE(dy && z && mean && invstd && sums && workspace && M > 0, B200_ERR_INVALID, "bn_bwd_reduce: bad argument");
   // activation-argument source: 2 = mask bits, 1 = y, 0 = recomputed from z (or no activation)
-  const int src = (act == B200_ACT_NONE) ? 0 : (act_mask != nullptr ? 2 : (y != nullptr ? 1 : 0));
+  const int src = pooled ? 3 : ((act == B200_ACT_NONE) ? 0 : (act_mask != nullptr ? 2 : (y != nullptr ? 1 : 0)));
 #define B200_RED_ARGS(VEC)                                                                                     \
   (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, act_mask, (const __nv_bfloat16*)z, M, C, rm.cv,           \
-      rm.rows_per_iter, act, mean, invstd, gamma, beta, partial
+      rm.rows_per_iter, act, mean, invstd, gamma, beta, partial, pg
 #define B200_LAUNCH_RED(VEC, ROWS, MINB)                                                                       \
   do {                                                                                                         \
     const RowMap rm = make_rowmap_v<VEC>(C);                                                                   \
     blocks = partial_blocks(M, rm, MINB);                                                                      \
-    if (src == 2)                                                                                              \
+    if (src == 3)                                                                                              \
+      b200::launch(bn_bwd_reduce_kernel<VEC, ROWS, MINB, 3>, blocks, kBnThreads, 0, stream, B200_RED_ARGS(VEC));         \
+    else if (src == 2)                                                                                         \
       b200::launch(bn_bwd_reduce_kernel<VEC, ROWS, MINB, 2>, blocks, kBnThreads, 0, stream, B200_RED_ARGS(VEC));         \
     else if (src == 1)                                                                                         \
       b200::launch(bn_bwd_reduce_kernel<VEC, ROWS, MINB, 1>, blocks, kBnThreads, 0, stream, B200_RED_ARGS(VEC));         \
@@ -679,7 +737,9 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* 
   cudaStream_t stream = (cudaStream_t)stream_;
   float* partial = workspace + kAccumFloats;
   int blocks = 0;
-  if (C > 1024) {
+  if (pooled) {                 // the gather needs registers: two rows in flight instead of four
+    B200_LAUNCH_RED(4, 2, 4);
+  } else if (C > 1024) {
     B200_LAUNCH_RED(8, 2, 3);
   } else {
     switch (bwd_variant()) {
@@ -698,29 +758,60 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* 
   return B200_OK;
 }
 
-extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M, int C,
-                              int act,
-                              const float* mean, const float* invstd, const float* gamma, const float* beta,
-                              const float* sums, void* dz, void* g_out, b200_stream_t stream_) {
+extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M,
+                                  int C, int act,
+                                  const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                  float* sums, float* dgamma_acc, float* dbeta_acc, float* workspace,
+                                  b200_stream_t stream_) {
+  return bn_bwd_reduce_impl(dy, y, act_mask, z, M, C, act, mean, invstd, gamma, beta, sums, dgamma_acc, dbeta_acc,
+                            workspace, stream_, false, PoolGeom{0, 0, 0, 0});
+}
+
+static int pooled_geom(int N, int H, int W, int C, const void* dp, const uint8_t* argmax, PoolGeom* pg) {
+  B200_REQUIRE(N > 0 && H > 1 && W > 1 && dp && argmax, B200_ERR_INVALID, "bn_bwd (pooled): bad argument");
+  B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "bn_bwd (pooled): C=%d must be a multiple of 8", C);
+  pg->H = H; pg->W = W; pg->OH = (H - 1) / 2 + 1; pg->OW = (W - 1) / 2 + 1;
+  return B200_OK;
+}
+
+extern "C" int b200_bn_bwd_reduce_pooled(const void* dp, const uint8_t* argmax, const void* z, int N, int H, int W, int C,
+                                         int act, const float* mean, const float* invstd, const float* gamma,
+                                         const float* beta, float* sums, float* dgamma_acc, float* dbeta_acc,
+                                         float* workspace, b200_stream_t stream_) {
+  PoolGeom pg;
+  int rc = pooled_geom(N, H, W, C, dp, argmax, &pg);
+  if (rc) return rc;
+  return bn_bwd_reduce_impl(dp, nullptr, argmax, z, (long long)N * H * W, C, act, mean, invstd, gamma, beta, sums,
+                            dgamma_acc, dbeta_acc, workspace, stream_, true, pg);
+}
+
+static int bn_bwd_dx_impl(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M, int C,
+                          int act, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                          const float* sums, void* dz, void* g_out, b200_stream_t stream_, bool pooled,
+                          const PoolGeom pg) {
   int rc = check_c(C, "bn_bwd_dx");
   if (rc) return rc;
   B200_REQUIRE(dy && z && mean && invstd && sums && dz && M > 0, B200_ERR_INVALID, "bn_bwd_dx: bad argument");
-  const int src = (act == B200_ACT_NONE) ? 0 : (act_mask != nullptr ? 2 : (y != nullptr ? 1 : 0));
+  const int src = pooled ? 3 : ((act == B200_ACT_NONE) ? 0 : (act_mask != nullptr ? 2 : (y != nullptr ? 1 : 0)));
 #define B200_DX_ARGS(VEC)                                                                                    \
   (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, act_mask, (const __nv_bfloat16*)z, M, C, rm.cv,         \
-      rm.rows_per_iter, act, mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out
+      rm.rows_per_iter, act, mean, invstd, gamma, beta, sums, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out, pg
 #define B200_LAUNCH_DX(VEC, ROWS, MINB)                                                                      \
   do {                                                                                                       \
     const RowMap rm = make_rowmap_v<VEC>(C);                                                                 \
     const int blocks = stream_blocks(M, rm);                                                                 \
-    if (src == 2)                                                                                            \
+    if (src == 3)                                                                                            \
+      b200::launch(bn_bwd_dx_kernel<VEC, ROWS, MINB, 3>, blocks, kBnThreads, 0, (cudaStream_t)stream_, B200_DX_ARGS(VEC)); \
+    else if (src == 2)                                                                                       \
       b200::launch(bn_bwd_dx_kernel<VEC, ROWS, MINB, 2>, blocks, kBnThreads, 0, (cudaStream_t)stream_, B200_DX_ARGS(VEC)); \
     else if (src == 1)                                                                                       \
       b200::launch(bn_bwd_dx_kernel<VEC, ROWS, MINB, 1>, blocks, kBnThreads, 0, (cudaStream_t)stream_, B200_DX_ARGS(VEC)); \
     else                                                                                                     \
       b200::launch(bn_bwd_dx_kernel<VEC, ROWS, MINB, 0>, blocks, kBnThreads, 0, (cudaStream_t)stream_, B200_DX_ARGS(VEC)); \
   } while (0)
-  if (C > 1024) {
+  if (pooled) {
+    B200_LAUNCH_DX(4, 2, 4);
+  } else if (C > 1024) {
     B200_LAUNCH_DX(8, 2, 3);
   } else {
     switch (bwd_variant()) {
@@ -734,4 +825,22 @@ extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const uint8_t* act_
 #undef B200_DX_ARGS
   B200_CHECK_LAUNCH("bn_bwd_dx_kernel");
   return B200_OK;
+}
+
+extern "C" int b200_bn_bwd_dx(const void* dy, const void* y, const uint8_t* act_mask, const void* z, long long M, int C,
+                              int act,
+                              const float* mean, const float* invstd, const float* gamma, const float* beta,
+                              const float* sums, void* dz, void* g_out, b200_stream_t stream_) {
+  return bn_bwd_dx_impl(dy, y, act_mask, z, M, C, act, mean, invstd, gamma, beta, sums, dz, g_out, stream_, false,
+                        PoolGeom{0, 0, 0, 0});
+}
+
+extern "C" int b200_bn_bwd_dx_pooled(const void* dp, const uint8_t* argmax, const void* z, int N, int H, int W, int C,
+                                     int act, const float* mean, const float* invstd, const float* gamma,
+                                     const float* beta, const float* sums, void* dz, b200_stream_t stream_) {
+  PoolGeom pg;
+  int rc = pooled_geom(N, H, W, C, dp, argmax, &pg);
+  if (rc) return rc;
+  return bn_bwd_dx_impl(dp, nullptr, argmax, z, (long long)N * H * W, C, act, mean, invstd, gamma, beta, sums, dz,
+                        nullptr, stream_, true, pg);
 }

@@ -20,9 +20,14 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// AFFINE: the pooled tensor is act(x * scale[c] + shift[c]) rounded to bf16 -- BatchNorm apply + ReLU + max pool of the
+// ImageNet stem in one pass (models/resnet.py:226-230), bit-identical to bn_apply followed by the plain pool, without
+// writing and re-reading the [N, 112, 112, 64] activation
+template <bool AFFINE>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W,
-                                                          int C, int OH, int OW, __nv_bfloat16* __restrict__ y,
-                                                          uint8_t* __restrict__ amax) {
+                                                          int C, int OH, int OW, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, int act,
+                                                          __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ amax) {
   pdl_wait();
   const int cv = C >> 3;
   const long long total = (long long)N * OH * OW * cv;
@@ -37,6 +42,16 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* _
     int bidx[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { best[i] = -CUDART_INF_F; bidx[i] = 0; }
+    float sc[8], sh[8];
+    if (AFFINE) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(scale + v * 8 + i));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(shift + v * 8 + i));
+        sc[i] = a.x; sc[i + 1] = a.y; sc[i + 2] = a.z; sc[i + 3] = a.w;
+        sh[i] = b.x; sh[i + 1] = b.y; sh[i + 2] = b.z; sh[i + 3] = b.w;
+      }
+    }
     bool first = true;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -48,6 +63,15 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* _
         if (w < 0 || w >= W) continue;
         float f[8];
         ld8(x + (((long long)n * H + h) * W + w) * C + v * 8, f);
+        if (AFFINE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a = fmaf(f[i], sc[i], sh[i]);
+            if (act == B200_ACT_RELU) a = fmaxf(a, 0.f);
+            else if (act == B200_ACT_RELU6) a = fminf(fmaxf(a, 0.f), 6.f);
+            f[i] = __bfloat162float(__float2bfloat16(a));     // the value bn_apply would have stored
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           // first occurrence wins on ties (strict >), NaN propagates, like ATen's max_pool2d
@@ -175,9 +199,21 @@ extern "C" int b200_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, 
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "maxpool_fwd: C=%d must be a multiple of 8", C);
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * OH * OW * (C / 8);
-  b200::launch(maxpool_fwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, N, H, W, C, OH,
-                                                                           OW, (__nv_bfloat16*)y, argmax);
+  b200::launch(maxpool_fwd_kernel<false>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, N, H,
+               W, C, OH, OW, nullptr, nullptr, 0, (__nv_bfloat16*)y, argmax);
   B200_CHECK_LAUNCH("maxpool_fwd_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_apply_maxpool3x3s2(const void* z, int N, int H, int W, int C, const float* scale,
+                                          const float* shift, int act, void* y, uint8_t* argmax, b200_stream_t stream) {
+  B200_REQUIRE(z && y && scale && shift && N > 0 && H > 0 && W > 0, B200_ERR_INVALID, "bn_apply_maxpool: bad argument");
+  B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "bn_apply_maxpool: C=%d must be a multiple of 8", C);
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * OH * OW * (C / 8);
+  b200::launch(maxpool_fwd_kernel<true>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)z, N, H,
+               W, C, OH, OW, scale, shift, act, (__nv_bfloat16*)y, argmax);
+  B200_CHECK_LAUNCH("maxpool_fwd_kernel<affine>");
   return B200_OK;
 }
 

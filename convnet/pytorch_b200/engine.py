@@ -31,6 +31,7 @@ FOLD_BN_EVAL = os.environ.get('B200_FOLD_BN_EVAL', '1') != '0'   # inference: BN
 BATCHED_TRANSPOSE = os.environ.get('B200_BATCHED_TRANSPOSE', '1') != '0'  # one launch for all dgrad weight layouts
 BN_ACT_MASK = os.environ.get('B200_BN_ACT_MASK', '0') != '0'    # 1-bit activation masks for residual joins (measured: not a win)
 FUSE_BN_STATS = os.environ.get('B200_FUSE_BN_STATS', '1') != '0'  # BN statistics in the conv epilogue
+FUSE_STEM_POOL = os.environ.get('B200_FUSE_STEM_POOL', '1') != '0'  # stem bn1+relu+maxpool in one pass, BN bwd gathers dp
 
 
 def _round_up(n, m):
@@ -450,6 +451,14 @@ class Runtime(object):
         u.y = None
         return u
 
+    def _sync_bn_sums(self, sums):
+        """SyncBatchNorm backward: the input gradient needs the GLOBAL d gamma / d beta sums divided by the global pixel
+        count; the kernel divides by the local count, so the reduced sums are pre-scaled by 1/world (equal per-rank
+        batches).  The arena gradients received the local sums and are averaged with all other gradients later."""
+        import torch.distributed as dist
+        dist.all_reduce(sums, group=self.sync_bn_group)
+        sums.mul_(1.0 / self.sync_bn_world)
+
     def _bn_bwd(self, u, dy, y_mask, act, want_g=False):
         """BN (+activation) backward of unit u: returns dz (and g = dy*act'(.) when want_g).
         y_mask=None with an activation: the mask is recomputed from z inside the kernels (no read of y)."""
@@ -458,12 +467,7 @@ class Runtime(object):
         ops.bn_bwd_reduce(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, bn.dgamma, bn.dbeta,
                           self._ws, act_mask=mask)
         if self.sync_bn_world > 1:
-            # the input gradient needs the GLOBAL d gamma / d beta sums divided by the global pixel count; the kernel
-            # divides by the local count, so the reduced sums are pre-scaled by 1/world (equal per-rank batches).  The
-            # arena gradients received the local sums above and are averaged with all other gradients later.
-            import torch.distributed as dist
-            dist.all_reduce(u.sums, group=self.sync_bn_group)
-            u.sums.mul_(1.0 / self.sync_bn_world)
+            self._sync_bn_sums(u.sums)
         g = torch.empty_like(dy) if want_g else None
         dz = ops.bn_bwd_dx(dy, y_mask, u.z, act, u.mean, u.invstd, bn.gamma, bn.beta, u.sums, g_out=g, act_mask=mask)
         return dz, g
@@ -786,19 +790,31 @@ class ResNetRuntime(Runtime):
         u = _Unit()
         u.conv, u.bn, u.act, u.x, u.desc = None, self.stem_bn, ACT_RELU, xs, desc
         self._conv_and_coeffs(u, xs, ws, training)
-        u.y = ops.bn_apply(u.z, u.scale, u.shift, ACT_RELU)
         st['unit'] = u
-        out = u.y
-        if self.has_maxpool:
-            out, st['argmax'] = ops.maxpool_fwd(u.y)
+        if self.has_maxpool and FUSE_STEM_POOL:
+            # bn1 -> relu -> maxpool in one pass: the [N, 112, 112, 64] activation is never written
+            u.y = None
+            out, st['argmax'] = ops.bn_apply_maxpool(u.z, u.scale, u.shift, ACT_RELU)
+        else:
+            u.y = ops.bn_apply(u.z, u.scale, u.shift, ACT_RELU)
+            out = u.y
+            if self.has_maxpool:
+                out, st['argmax'] = ops.maxpool_fwd(u.y)
         st['cin'] = Cin
         return out, st
 
     def _stem_bwd(self, st, dy):
         u = st['unit']
-        if self.has_maxpool:
-            dy = ops.maxpool_bwd(dy, st['argmax'], tuple(u.y.shape))
-        dz, _ = self._bn_bwd(u, dy, None, ACT_RELU)
+        if self.has_maxpool and u.y is None:
+            # the BN backward kernels gather the pre-pool gradient from dy through the argmax bytes
+            bn = u.bn
+            dz = ops.bn_bwd_pooled(dy, st['argmax'], u.z, ACT_RELU, u.mean, u.invstd, bn.gamma, bn.beta, u.sums,
+                                   bn.dgamma, bn.dbeta, self._ws,
+                                   sums_hook=self._sync_bn_sums if self.sync_bn_world > 1 else None)
+        else:
+            if self.has_maxpool:
+                dy = ops.maxpool_bwd(dy, st['argmax'], tuple(u.y.shape))
+            dz, _ = self._bn_bwd(u, dy, None, ACT_RELU)
         K, Cin = self.stem_conv.out_channels, st['cin']
         def stem_wgrad():   # every wgrad shares the split-K workspace: all of them go through _wgrad_async
             if self.imagenet_stem:

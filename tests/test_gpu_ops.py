@@ -148,6 +148,55 @@ def test_maxpool(N, H, W, C):
     assert close_bf16(dx.permute(0, 3, 1, 2), dxr, 2 ** -7)
 
 
+@pytest.mark.parametrize("N,H,W,C", [(4, 112, 112, 64), (3, 17, 23, 16), (2, 9, 8, 128)])
+def test_stem_bn_relu_maxpool_fused(N, H, W, C):
+    """ImageNet stem tail (models/resnet.py:226-230 of the reference: bn1 -> relu -> maxpool) as two fused passes:
+    forward bit-identical to bn_apply + maxpool_fwd; backward (BN kernels gathering the pooled gradient through the
+    argmax bytes) against fp64 autograd of the same function and against the unfused kernel chain."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    z = (torch.randn(N, H, W, C, generator=g) * 1.5 + 0.3).cuda().to(bf16)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.3).cuda()
+    gamma[::5] *= -1.0                                    # negative scales: max(relu(s*z+b)) is not monotone in z
+    ws = torch.zeros(ops.bn_workspace_floats(C)).cuda()
+    mean, invstd, scale, shift = [torch.empty(C).cuda() for _ in range(4)]
+    ops.bn_stats(z, gamma, beta, 1e-5, 0.1, None, None, None, mean, invstd, scale, shift, ws)
+    a = ops.bn_apply(z, scale, shift, 1)
+    p_ref, am_ref = ops.maxpool_fwd(a)
+    p, am = ops.bn_apply_maxpool(z, scale, shift, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(p, p_ref) and torch.equal(am, am_ref)
+
+    dp = torch.randn(p.shape, generator=g).cuda().to(bf16)
+    sums, dgam, dbet = torch.empty(2 * C).cuda(), torch.zeros(C).cuda(), torch.zeros(C).cuda()
+    dz = ops.bn_bwd_pooled(dp, am, z, 1, mean, invstd, gamma, beta, sums, dgam, dbet, ws)
+    # unfused chain (rounds the pre-pool gradient to bf16 in between)
+    da = ops.maxpool_bwd(dp, am, (N, H, W, C))
+    sums_u, dg_u, db_u = torch.empty(2 * C).cuda(), torch.zeros(C).cuda(), torch.zeros(C).cuda()
+    ops.bn_bwd_reduce(da, None, z, 1, mean, invstd, gamma, beta, sums_u, dg_u, db_u, ws)
+    dz_u = ops.bn_bwd_dx(da, None, z, 1, mean, invstd, gamma, beta, sums_u)
+    torch.cuda.synchronize()
+    # fp64 reference with the kernel's routing: gradient to the stored argmax element, ReLU mask on the fp32 argument
+    zd = z.double().view(-1, C).requires_grad_(True)
+    mu, var = zd.mean(0), zd.var(0, unbiased=False)
+    xhat = (zd - mu) / torch.sqrt(var + 1e-5)
+    pre = xhat * gamma.double() + beta.double()
+    gd = torch.zeros(N, H, W, C, dtype=torch.float64, device='cuda')
+    n_i, p_i, q_i, c_i = torch.meshgrid(torch.arange(N), torch.arange(p.shape[1]), torch.arange(p.shape[2]),
+                                        torch.arange(C), indexing='ij')
+    n_i, p_i, q_i, c_i = [t.cuda() for t in (n_i, p_i, q_i, c_i)]
+    hh = 2 * p_i - 1 + am.long() // 3
+    ww = 2 * q_i - 1 + am.long() % 3
+    gd.index_put_((n_i, hh, ww, c_i), dp.double(), accumulate=True)
+    mask = ((z.float() * scale + shift) > 0).double()
+    gd = (gd * mask).view(-1, C)
+    dz_ref, = torch.autograd.grad(pre, zd, gd)
+    tol = 1e-5 * math.sqrt(max(N * H * W, 1e4) / 1e4) * 10
+    assert rel(dgam, (gd * xhat.detach()).sum(0)) < tol and rel(dbet, gd.sum(0)) < tol
+    assert close_bf16(dz.view(-1, C), dz_ref)
+    assert rel(dg_u, dgam) < 1e-2 and rel(db_u, dbet) < 1e-2 and rel(dz_u.float(), dz.float()) < 1e-2
+
+
 def test_avgpool():
     ops = _ops()
     x = torch.randn(5, 7, 7, 256).cuda().to(bf16)
