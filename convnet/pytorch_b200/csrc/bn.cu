@@ -273,6 +273,25 @@ __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* be
   shift[c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
 }
 
+// Activation-mask layout ("row quads"): the bytes of rows 4q..4q+3 for one 8-channel vector form ONE 32-bit word,
+// word index q * (C/8) + v8.  A backward thread that owns ROWS consecutive rows fetches their masks with a single
+// 16/32-bit load -- with a plain [row][C/8] byte layout every row cost its own load instruction, and the kernels are
+// bound by requests in flight, not by bytes (that version was slower than re-reading the bf16 output).
+__device__ __forceinline__ long long mask_byte_index(long long row, int cv8, int v8) {
+  return (((row >> 2) * cv8 + v8) << 2) + (row & 3);
+}
+// mask bytes of rows [row0, row0 + ROWS) (row0 % ROWS == 0, ROWS in {2, 4, 8}) for vector v8: byte u = row row0 + u
+template <int ROWS>
+__device__ __forceinline__ unsigned long long mask_rows(const uint8_t* __restrict__ amask, long long row0, int cv8,
+                                                        int v8) {
+  const uint8_t* p = amask + mask_byte_index(row0, cv8, v8);
+  if (ROWS == 2) return __ldg(reinterpret_cast<const unsigned short*>(p));
+  if (ROWS == 4) return __ldg(reinterpret_cast<const unsigned int*>(p));
+  const unsigned long long lo = __ldg(reinterpret_cast<const unsigned int*>(p));
+  const unsigned long long hi = __ldg(reinterpret_cast<const unsigned int*>(p + 4LL * cv8));
+  return lo | (hi << 32);
+}
+
 // ---- forward apply ------------------------------------------------------------------------------
 template <int MODE>  // 0: none, 1: + residual, 2: + (z2*scale2+shift2)
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
@@ -317,8 +336,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
     store8(y + ra * C + v * 8, fa);
     if (hb) store8(y + rb * C + v * 8, fb);
     if (act_mask != nullptr) {   // one byte per (row, 8-channel vector): bit i = act'(.) of channel v*8+i
-      act_mask[ra * cv + v] = static_cast<uint8_t>(ma);
-      if (hb) act_mask[rb * cv + v] = static_cast<uint8_t>(mb);
+      act_mask[mask_byte_index(ra, cv, v)] = static_cast<uint8_t>(ma);
+      if (hb) act_mask[mask_byte_index(rb, cv, v)] = static_cast<uint8_t>(mb);
     }
   }
 }
@@ -426,9 +445,11 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
   const int t = threadIdx.x;
   const bool active = t < rows_per_iter * cv;
   const int r0 = t / cv, v = t - r0 * cv;
-  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  // SRC 2 (mask words): a thread owns ROWS CONSECUTIVE rows (one mask load); block ranges are multiples of 8 rows
+  const long long rows_per_block = SRC == 2 ? (((M + gridDim.x - 1) / gridDim.x + 7) & ~7LL) : (M + gridDim.x - 1) / gridDim.x;
   const long long row_begin = blockIdx.x * rows_per_block;
   const long long row_end = min(M, row_begin + rows_per_block);
+  constexpr long long kRowStep = SRC == 2 ? 1 : 0;       // distance between a thread's rows: 1 or rows_per_iter
   float acc[2 * VEC];
 #pragma unroll
   for (int i = 0; i < 2 * VEC; ++i) acc[i] = 0.f;
@@ -447,33 +468,35 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_reduce_kernel(
       }
     }
     const long long col = (long long)v * VEC;
-    for (long long r = row_begin + r0; r < row_end; r += (long long)ROWS * rows_per_iter) {
+    const long long rstep = kRowStep ? 1 : rows_per_iter;
+    for (long long r = row_begin + (kRowStep ? (long long)r0 * ROWS : r0); r < row_end;
+         r += (long long)ROWS * rows_per_iter) {
       RawVec<VEC> rd[ROWS], rz[ROWS], ry[ROWS];
-      uint32_t rm[ROWS];
+      unsigned long long rm = 0;
       bool ok[ROWS];
+      if (SRC == 2) rm = mask_rows<ROWS>(amask, r, C >> 3, (int)(col >> 3)) >> (col & 7 & ~(VEC - 1));
 #pragma unroll
       for (int u = 0; u < ROWS; ++u) {
-        const long long rr = r + (long long)u * rows_per_iter;
+        const long long rr = r + (long long)u * rstep;
         ok[u] = rr < row_end;
         if (ok[u]) {
           if (SRC != 3) rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
           rz[u] = ldv(z + rr * C + col, (RawVec<VEC>*)nullptr);
           if (SRC == 1) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
-          if (SRC == 2) rm[u] = static_cast<uint32_t>(__ldg(amask + ((rr * C + col) >> 3))) >> (col & 7 & ~(VEC - 1));
         }
       }
 #pragma unroll
       for (int u = 0; u < ROWS; ++u) {
         if (!ok[u]) continue;
         float da[VEC], za[VEC], ya[VEC];
-        if (SRC == 3) pool_gather<VEC>(dy, amask, r + (long long)u * rows_per_iter, col, C, pg, da);
+        if (SRC == 3) pool_gather<VEC>(dy, amask, r + (long long)u * rstep, col, C, pg, da);
         else unpackv(rd[u], da);
         unpackv(rz[u], za);
         if (SRC == 1) unpackv(ry[u], ya);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           float g = da[i];
-          if (SRC == 2) g = ((rm[u] >> i) & 1u) ? g : 0.f;
+          if (SRC == 2) g = ((rm >> (8 * u + i)) & 1ull) ? g : 0.f;
           else if (act != B200_ACT_NONE) g *= act_mask(SRC == 1 ? ya[i] : fmaf(za[i], sc[i], sh[i]), act);
           acc[i] = fmaf(g, za[i] - mu[i], acc[i]);   // the 1/std factor is applied once per channel below
           acc[VEC + i] += g;
@@ -549,9 +572,10 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
   const int t = threadIdx.x;
   if (t >= rows_per_iter * cv) return;
   const int r0 = t / cv, v = t - r0 * cv;
-  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long rows_per_block = SRC == 2 ? (((M + gridDim.x - 1) / gridDim.x + 7) & ~7LL) : (M + gridDim.x - 1) / gridDim.x;
   const long long row_begin = blockIdx.x * rows_per_block;
   const long long row_end = min(M, row_begin + rows_per_block);
+  constexpr long long kRowStep = SRC == 2 ? 1 : 0;       // as in bn_bwd_reduce_kernel
   // dz = A*g + B*z + Cc  with A = gamma*istd, B = -gamma*istd^2*dgamma/M, Cc = -A*dbeta/M - B*mean;
   // the activation argument recomputed from z is z*A + sh
   float A[VEC], B[VEC], Cc[VEC], sh[VEC];
@@ -574,25 +598,27 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
     }
   }
   const long long col = (long long)v * VEC;
-  for (long long r = row_begin + r0; r < row_end; r += (long long)ROWS * rows_per_iter) {
+  const long long rstep = kRowStep ? 1 : rows_per_iter;
+  for (long long r = row_begin + (kRowStep ? (long long)r0 * ROWS : r0); r < row_end;
+       r += (long long)ROWS * rows_per_iter) {
     RawVec<VEC> rd[ROWS], rz[ROWS], ry[ROWS];
-    uint32_t rm[ROWS];
+    unsigned long long rm = 0;
     bool ok[ROWS];
+    if (SRC == 2) rm = mask_rows<ROWS>(amask, r, C >> 3, (int)(col >> 3)) >> (col & 7 & ~(VEC - 1));
 #pragma unroll
     for (int u = 0; u < ROWS; ++u) {
-      const long long rr = r + (long long)u * rows_per_iter;
+      const long long rr = r + (long long)u * rstep;
       ok[u] = rr < row_end;
       if (ok[u]) {
         if (SRC != 3) rd[u] = ldv(dy + rr * C + col, (RawVec<VEC>*)nullptr);
         rz[u] = ldv(z + rr * C + col, (RawVec<VEC>*)nullptr);
         if (SRC == 1) ry[u] = ldv(y + rr * C + col, (RawVec<VEC>*)nullptr);
-        if (SRC == 2) rm[u] = static_cast<uint32_t>(__ldg(amask + ((rr * C + col) >> 3))) >> (col & 7 & ~(VEC - 1));
       }
     }
 #pragma unroll
     for (int u = 0; u < ROWS; ++u) {
       if (!ok[u]) continue;
-      const long long rr = r + (long long)u * rows_per_iter;
+      const long long rr = r + (long long)u * rstep;
       float da[VEC], za[VEC], ya[VEC];
       if (SRC == 3) pool_gather<VEC>(dy, amask, rr, col, C, pg, da);
       else unpackv(rd[u], da);
@@ -601,7 +627,7 @@ __global__ void __launch_bounds__(kBnThreads, MINB) bn_bwd_dx_kernel(
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         float g = da[i];
-        if (SRC == 2) g = ((rm[u] >> i) & 1u) ? g : 0.f;
+        if (SRC == 2) g = ((rm >> (8 * u + i)) & 1ull) ? g : 0.f;
         else if (act != B200_ACT_NONE) g *= act_mask(SRC == 1 ? ya[i] : fmaf(za[i], A[i], sh[i]), act);
         da[i] = g;
         za[i] = A[i] * g + B[i] * za[i] + Cc[i];
@@ -638,6 +664,8 @@ static inline unsigned* ws_ticket(float* ws) { return reinterpret_cast<unsigned*
 using namespace b200;
 
 extern "C" size_t b200_bn_workspace_floats(int C) { (void)C; return (size_t)kWsFloats; }
+// rows padded to a multiple of 8: the backward kernels read whole row-quad words (two of them with 8 rows in flight)
+extern "C" size_t b200_bn_act_mask_bytes(long long M, int C) { return (size_t)((M + 7) / 8 * 8) * (size_t)(C / 8); }
 
 extern "C" int b200_bn_stats(const void* z, long long M, int C, const float* gamma, const float* beta, float eps,
                              float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,

@@ -386,7 +386,8 @@ class Runtime(object):
         # element instead of re-reading the bf16 output in both backward kernels
         u.mask = None
         if BN_ACT_MASK and tape and training and act != ACT_NONE and (other is not None or residual is not None):
-            u.mask = torch.empty(u.z.numel() // 8, device=self.device, dtype=torch.uint8)
+            u.mask = torch.empty(ops.bn_act_mask_bytes(u.z.numel() // u.z.shape[-1], u.z.shape[-1]), device=self.device,
+                                 dtype=torch.uint8)
         if other is not None:
             u.y = ops.bn_apply(u.z, u.scale, u.shift, act, z2=other.z, scale2=other.scale, shift2=other.shift,
                                act_mask=u.mask)

@@ -43,6 +43,7 @@ SIGNATURES = {
     "b200_dwconv_dgrad": [_dp, _vp, _vp, _vp, _vp],
     "b200_dwconv_wgrad": [_dp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_bn_workspace_floats": [_i],
+    "b200_bn_act_mask_bytes": [_ll, _i],
     "b200_bn_stats": [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_bn_finalize": [_ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200_bn_eval_coeffs": [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp],
@@ -82,7 +83,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"b200_last_error": ctypes.c_char_p, "b200_launch_count": ctypes.c_longlong,
              "b200_conv_wgrad_workspace_bytes": ctypes.c_size_t,
-             "b200_bn_workspace_floats": ctypes.c_size_t}
+             "b200_bn_workspace_floats": ctypes.c_size_t, "b200_bn_act_mask_bytes": ctypes.c_size_t}
 
 _lib = None
 _lock = threading.Lock()

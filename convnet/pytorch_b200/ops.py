@@ -183,6 +183,11 @@ def bn_workspace_floats(C):
     return int(_l.load().b200_bn_workspace_floats(int(C)))
 
 
+def bn_act_mask_bytes(M, C):
+    """bytes of the 1-bit activation mask of an [M, C] tensor (rows padded to 8: the kernels read whole row-quad words)"""
+    return (int(M) + 7) // 8 * 8 * (int(C) // 8)
+
+
 def bn_stats(z, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd, scale, shift, workspace):
     C = z.shape[-1]
     M = z.numel() // C
@@ -217,8 +222,8 @@ def bn_apply(z, scale, shift, act=ACT_NONE, residual=None, z2=None, scale2=None,
     C = z.shape[-1]
     M = z.numel() // C
     _chk(z, bf16, "z"); _chk(residual, bf16, "residual"); _chk(z2, bf16, "z2"); _chk(act_mask, torch.uint8, "act_mask")
-    if act_mask is not None and act_mask.numel() * 8 != z.numel():
-        raise _l.B200Error("act_mask must hold z.numel()/8 bytes")
+    if act_mask is not None and act_mask.numel() != bn_act_mask_bytes(M, C):
+        raise _l.B200Error("act_mask must hold bn_act_mask_bytes(M, C) bytes")
     if out is None:
         out = torch.empty_like(z)
     with _T('bn_apply', 0, 2 * z.numel() * (2 + (residual is not None) + (z2 is not None))):

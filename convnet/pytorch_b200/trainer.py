@@ -266,7 +266,13 @@ class Trainer(object):
         # with NCCL all-reduces inside the capture, ProcessGroupNCCL's watchdog thread polls CUDA events concurrently: the
         # default "global" capture mode would treat that as a capture violation
         mode = 'thread_local' if self.b200.grad_bucket_hook is not None else 'global'
-        with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode=mode):
+        # capture on a HIGH-priority stream: the kernel nodes inherit it, so when a main-chain kernel (BN backward ->
+        # dgrad of the next unit) and a side-stream weight gradient become ready together the block scheduler starts the
+        # critical one first and the wgrad CTAs fill in beside the HBM-bound BN kernels that follow
+        if getattr(self, '_capture_stream', None) is None:
+            prio = -1 if os.environ.get('B200_MAIN_PRIORITY', '0') != '0' else 0
+            self._capture_stream = torch.cuda.Stream(device=x_s.device, priority=prio)
+        with torch.cuda.graph(graph, pool=self._graph_pool, stream=self._capture_stream, capture_error_mode=mode):
             stats = None
             if eps is not None:            # the whole step is library calls: nothing of autograd inside the graph
                 out, stats = self.b200.train_step(x_s, y_s, eps, up)

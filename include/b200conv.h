@@ -111,8 +111,11 @@ int b200_bn_finalize(long long M, int C, const float* gamma, const float* beta, 
 int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float* scale, float* shift, b200_stream_t stream);
 /* y = act(z*scale+shift + [residual | z2*scale2+shift2]) */
-/* act_mask (nullable, M*C/8 bytes): bit c%8 of byte (row*C + c)/8 = act'(.) of that element (1 where the
- * activation passes the gradient).  The backward kernels accept it instead of y: 1 bit instead of 16 per element. */
+/* act_mask (nullable, b200_bn_act_mask_bytes(M, C) bytes): one bit per element = act'(.) (1 where the activation
+ * passes the gradient).  Layout "row quads": the byte of (row, 8-channel vector v8) -- bit c%8 -- is byte row%4 of the
+ * 32-bit word (row/4)*(C/8) + v8, so a backward thread fetches the masks of its 2/4/8 consecutive rows with one load.
+ * The backward kernels accept it instead of y: 1 bit instead of 16 per element. */
+size_t b200_bn_act_mask_bytes(long long M, int C);
 int b200_bn_apply(const void* z, long long M, int C, const float* scale, const float* shift,
                   const void* residual, const void* z2, const float* scale2, const float* shift2,
                   int act, void* y, uint8_t* act_mask, b200_stream_t stream);

@@ -80,11 +80,13 @@ def test_bn_forward_backward(M, C, act):
     # 1-bit activation masks written by bn_apply replace y in both backward kernels.  The bits test the fp32
     # PRE-activation value (like torch's relu/hardtanh backward); they may differ from the mask derived from the
     # bf16-rounded output only where the output rounds onto a clamp boundary.
-    bits = torch.zeros(M * C // 8, dtype=torch.uint8).cuda()
+    bits = torch.zeros(ops.bn_act_mask_bytes(M, C), dtype=torch.uint8).cuda()
     y2 = ops.bn_apply(z, scale, shift, act, residual=res, act_mask=bits)
     assert torch.equal(y2, y)
     shifts = torch.arange(8, device='cuda', dtype=torch.int32)
-    mask2 = ((bits.view(M, C // 8, 1).to(torch.int32) >> shifts) & 1).view(M, C).double()
+    # "row quad" layout: byte (row % 4) of word (row // 4) * (C / 8) + v8
+    by_row = bits.view(-1, C // 8, 4).permute(0, 2, 1).reshape(-1, C // 8)[:M]
+    mask2 = ((by_row.reshape(M, C // 8, 1).to(torch.int32) >> shifts) & 1).view(M, C).double()
     assert float((mask2 != mask).double().mean()) < 2e-3
     if act != 2:
         assert torch.equal(mask2, mask)
