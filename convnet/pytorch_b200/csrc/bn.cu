@@ -390,10 +390,11 @@ struct PoolGeom {
 template <int VEC>
 __device__ __forceinline__ void pool_gather(const __nv_bfloat16* __restrict__ dp, const uint8_t* __restrict__ amax,
                                             long long row, long long col, int C, const PoolGeom& pg, float (&g)[VEC]) {
-  const int w = (int)(row % pg.W);
-  const long long t = row / pg.W;
-  const int h = (int)(t % pg.H);
-  const long long n = t / pg.H;
+  const unsigned r32 = (unsigned)row;                 // the host checks N*H*W < 2^31: 32-bit div/mod
+  const int w = (int)(r32 % (unsigned)pg.W);
+  const unsigned t = r32 / (unsigned)pg.W;
+  const int h = (int)(t % (unsigned)pg.H);
+  const long long n = t / (unsigned)pg.H;
   const int p_lo = h >> 1, q_lo = w >> 1;
   uint32_t ab[4][VEC / 4];
   uint32_t gr[4][VEC / 2];
@@ -798,6 +799,7 @@ extern "C" int b200_bn_bwd_reduce(const void* dy, const void* y, const uint8_t* 
 static int pooled_geom(int N, int H, int W, int C, const void* dp, const uint8_t* argmax, PoolGeom* pg) {
   B200_REQUIRE(N > 0 && H > 1 && W > 1 && dp && argmax, B200_ERR_INVALID, "bn_bwd (pooled): bad argument");
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "bn_bwd (pooled): C=%d must be a multiple of 8", C);
+  B200_REQUIRE((long long)N * H * W < (1LL << 31), B200_ERR_UNSUPPORTED, "bn_bwd (pooled): tensor too large");
   pg->H = H; pg->W = W; pg->OH = (H - 1) / 2 + 1; pg->OW = (W - 1) / 2 + 1;
   return B200_OK;
 }

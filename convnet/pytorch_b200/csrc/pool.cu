@@ -30,14 +30,14 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* _
                                                           __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ amax) {
   pdl_wait();
   const int cv = C >> 3;
-  const long long total = (long long)N * OH * OW * cv;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % cv);
-    long long pix = idx / cv;
-    const int q = (int)(pix % OW); pix /= OW;
-    const int p = (int)(pix % OH);
-    const int n = (int)(pix / OH);
+  // 32-bit index arithmetic (the host checks N*H*W*C/8 < 2^31): 64-bit div/mod cost more than the loads
+  const unsigned total = (unsigned)N * OH * OW * cv;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int v = (int)(idx % (unsigned)cv);
+    unsigned pix = idx / (unsigned)cv;
+    const int q = (int)(pix % (unsigned)OW); pix /= (unsigned)OW;
+    const int p = (int)(pix % (unsigned)OH);
+    const int n = (int)(pix / (unsigned)OH);
     float best[8];
     int bidx[8];
 #pragma unroll
@@ -96,14 +96,13 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
                                                           int OH, int OW, __nv_bfloat16* __restrict__ dx) {
   pdl_wait();
   const int cv = C >> 3;
-  const long long total = (long long)N * H * W * cv;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % cv);
-    long long pix = idx / cv;
-    const int w = (int)(pix % W); pix /= W;
-    const int h = (int)(pix % H);
-    const int n = (int)(pix / H);
+  const unsigned total = (unsigned)N * H * W * cv;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int v = (int)(idx % (unsigned)cv);
+    unsigned pix = idx / (unsigned)cv;
+    const int w = (int)(pix % (unsigned)W); pix /= (unsigned)W;
+    const int h = (int)(pix % (unsigned)H);
+    const int n = (int)(pix / (unsigned)H);
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -197,6 +196,7 @@ extern "C" int b200_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, 
                                      b200_stream_t stream) {
   B200_REQUIRE(x && y && N > 0 && H > 0 && W > 0, B200_ERR_INVALID, "maxpool_fwd: bad argument");
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "maxpool_fwd: C=%d must be a multiple of 8", C);
+  B200_REQUIRE((long long)N * H * W * (C / 8) < (1LL << 31), B200_ERR_UNSUPPORTED, "maxpool_fwd: tensor too large");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * OH * OW * (C / 8);
   b200::launch(maxpool_fwd_kernel<false>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, N, H,
@@ -209,6 +209,7 @@ extern "C" int b200_bn_apply_maxpool3x3s2(const void* z, int N, int H, int W, in
                                           const float* shift, int act, void* y, uint8_t* argmax, b200_stream_t stream) {
   B200_REQUIRE(z && y && scale && shift && N > 0 && H > 0 && W > 0, B200_ERR_INVALID, "bn_apply_maxpool: bad argument");
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "bn_apply_maxpool: C=%d must be a multiple of 8", C);
+  B200_REQUIRE((long long)N * H * W * (C / 8) < (1LL << 31), B200_ERR_UNSUPPORTED, "bn_apply_maxpool: tensor too large");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * OH * OW * (C / 8);
   b200::launch(maxpool_fwd_kernel<true>, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)z, N, H,
@@ -221,6 +222,7 @@ extern "C" int b200_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, int 
                                      b200_stream_t stream) {
   B200_REQUIRE(dy && argmax && dx && N > 0, B200_ERR_INVALID, "maxpool_bwd: bad argument");
   B200_REQUIRE(C % 8 == 0, B200_ERR_UNSUPPORTED, "maxpool_bwd: C=%d must be a multiple of 8", C);
+  B200_REQUIRE((long long)N * H * W * (C / 8) < (1LL << 31), B200_ERR_UNSUPPORTED, "maxpool_bwd: tensor too large");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * H * W * (C / 8);
   b200::launch(maxpool_bwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, argmax, N, H, W,
