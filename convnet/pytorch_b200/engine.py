@@ -29,9 +29,15 @@ HALO_STEM_WGRAD = os.environ.get('B200_HALO_STEM_WGRAD', '1') != '0'
 WGRAD_STREAM = os.environ.get('B200_WGRAD_STREAM', '1') != '0'   # weight gradients on a second CUDA stream
 FOLD_BN_EVAL = os.environ.get('B200_FOLD_BN_EVAL', '1') != '0'   # inference: BN folded into conv weights + epilogue bias
 BATCHED_TRANSPOSE = os.environ.get('B200_BATCHED_TRANSPOSE', '1') != '0'  # one launch for all dgrad weight layouts
-BN_ACT_MASK = os.environ.get('B200_BN_ACT_MASK', '0') != '0'    # 1-bit activation masks for residual joins (measured: not a win)
+# 1-bit activation masks for residual joins, packed in row-quad words: the BN backward kernels read 1 bit instead of the
+# bf16 output per element with ONE extra load per thread and iteration (measured: -0.74 ms/step on ResNet-50)
+BN_ACT_MASK = os.environ.get('B200_BN_ACT_MASK', '1') != '0'
 FUSE_BN_STATS = os.environ.get('B200_FUSE_BN_STATS', '1') != '0'  # BN statistics in the conv epilogue
-FUSE_STEM_POOL = os.environ.get('B200_FUSE_STEM_POOL', '1') != '0'  # stem bn1+relu+maxpool in one pass, BN bwd gathers dp
+# stem bn1+relu+maxpool: 0 = three kernels, 1 (default) = one forward pass (the 112x112 activation is never written),
+# backward through maxpool_bwd + the plain BN kernels; 2 = also the BN backward kernels gather the pooled gradient
+# through the argmax bytes (no materialised pre-pool gradient) -- measured SLOWER (+0.4 ms: the kernels are bound by
+# load requests in flight and the gather replaces one streaming load by 4.5 cached ones)
+FUSE_STEM_POOL = int(os.environ.get('B200_FUSE_STEM_POOL', '1'))
 
 
 def _round_up(n, m):
@@ -806,7 +812,7 @@ class ResNetRuntime(Runtime):
 
     def _stem_bwd(self, st, dy):
         u = st['unit']
-        if self.has_maxpool and u.y is None:
+        if self.has_maxpool and u.y is None and FUSE_STEM_POOL >= 2:
             # the BN backward kernels gather the pre-pool gradient from dy through the argmax bytes
             bn = u.bn
             dz = ops.bn_bwd_pooled(dy, st['argmax'], u.z, ACT_RELU, u.mean, u.invstd, bn.gamma, bn.beta, u.sums,
@@ -814,8 +820,8 @@ class ResNetRuntime(Runtime):
                                    sums_hook=self._sync_bn_sums if self.sync_bn_world > 1 else None)
         else:
             if self.has_maxpool:
-                dy = ops.maxpool_bwd(dy, st['argmax'], tuple(u.y.shape))
-            dz, _ = self._bn_bwd(u, dy, None, ACT_RELU)
+                dy = ops.maxpool_bwd(dy, st['argmax'], tuple(u.z.shape))
+            dz, _ = self._bn_bwd(u, dy, None, ACT_RELU)   # mask recomputed from z: the activation is not needed
         K, Cin = self.stem_conv.out_channels, st['cin']
         def stem_wgrad():   # every wgrad shares the split-K workspace: all of them go through _wgrad_async
             if self.imagenet_stem:

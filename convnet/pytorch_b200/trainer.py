@@ -270,7 +270,7 @@ class Trainer(object):
         # dgrad of the next unit) and a side-stream weight gradient become ready together the block scheduler starts the
         # critical one first and the wgrad CTAs fill in beside the HBM-bound BN kernels that follow
         if getattr(self, '_capture_stream', None) is None:
-            prio = -1 if os.environ.get('B200_MAIN_PRIORITY', '0') != '0' else 0
+            prio = -1 if os.environ.get('B200_MAIN_PRIORITY', '1') != '0' else 0
             self._capture_stream = torch.cuda.Stream(device=x_s.device, priority=prio)
         with torch.cuda.graph(graph, pool=self._graph_pool, stream=self._capture_stream, capture_error_mode=mode):
             stats = None
