@@ -338,8 +338,11 @@ def test_sumsq_and_grad_coef():
     assert abs(float(out[1]) - run / (2 * norm + 1e-6)) < 1e-5
 
 
-@pytest.mark.parametrize("N,H,C,stride", [(2, 28, 96, 1), (2, 56, 144, 2), (1, 7, 960, 1), (3, 14, 24, 2)])
+@pytest.mark.parametrize("N,H,C,stride", [(2, 28, 96, 1), (2, 56, 144, 2), (1, 7, 960, 1), (3, 14, 24, 2), (5, 7, 576, 2),
+                                          (4, 19, 32, 1), (2, 37, 16, 2), (33, 112, 32, 1), (9, 112, 96, 2), (40, 4, 1024, 1)])
 def test_depthwise(N, H, C, stride):
+    """depthwise 3x3 (sliding-window kernels for stride 1 / 2; odd map sizes exercise the row / column tails, maps taller
+    than 16 rows the chunking, large N the grid-stride loops)"""
     ops = _ops()
     x = torch.randn(N, H, H, C).cuda().to(bf16)
     w = (torch.randn(9, C) / 3).cuda().to(bf16)
