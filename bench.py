@@ -339,7 +339,7 @@ def main():
             if key and default_cfg_for_traffic(args):
                 roof['traffic'] = (tj[key]['dram_read_bytes'] + tj[key]['dram_write_bytes']) / max(tj[key]['launches'], 1)
                 roof['traffic_unit'] = 'bytes per launch (class average; ncu, profiles/r02_traffic.json)'
-                roof['algorithmic_bytes_per_launch'] = None
+                roof['algorithmic_bytes_per_launch'] = d['bytes'] / max(d['calls'], 1) if d.get('bytes') else None
         except Exception:
             pass
         roof['peak_source'] = pk['source'] + (' sustained' if dom.startswith('conv_') else '')

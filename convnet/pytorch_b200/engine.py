@@ -966,7 +966,9 @@ class MobileNetRuntime(Runtime):
 
     def _mb_conv_bwd(self, kind, u, dz, need_dx=True, residual=None):
         if kind == 'dw':
-            ops.dwconv_wgrad(u.x, dz, u.desc, u.conv.g32, self._dw_ws)
+            # like the dense weight gradients: on the side stream (all depthwise wgrads share _dw_ws, the stream orders
+            # them), off the BN-backward -> dgrad chain
+            self._wgrad_async(lambda: ops.dwconv_wgrad(u.x, dz, u.desc, u.conv.g32, self._dw_ws), u.x, dz)
             return ops.dwconv_dgrad(dz, u.conv.w16, u.desc) if need_dx else None
         return self._conv_bwd(u, dz, need_dx=need_dx, residual=residual)
 

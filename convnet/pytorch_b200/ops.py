@@ -72,6 +72,14 @@ def _conv_flops(d):
     return 2 * d.N * d.P * d.Q * macs
 
 
+def _conv_bytes(x, w, out, residual=None):
+    """ALGORITHMIC bytes of one convolution launch: every operand tensor once (input, weights, output, residual)."""
+    n = x.numel() * x.element_size() + w.numel() * w.element_size() + out.numel() * out.element_size()
+    if residual is not None:
+        n += residual.numel() * residual.element_size()
+    return n
+
+
 def _chk(t, dtype, name):
     if t is None:
         return
@@ -114,7 +122,7 @@ def conv_fprop(x, w, desc, out=None, bias=None, residual=None, act=ACT_NONE, out
         out = torch.empty((desc.N, desc.P, desc.Q, desc.K), device=x.device,
                           dtype=torch.float32 if out_fp32 else bf16)
     ep = Epilogue(_l.ptr(bias), _l.ptr(residual), int(act), int(bool(out_fp32)), _l.ptr(bn_stats_ws))
-    with _T('conv_fprop', _conv_flops(desc), 0):
+    with _T('conv_fprop', _conv_flops(desc), _conv_bytes(x, w, out, residual)):
         _l.check(_l.load().b200_conv_fprop(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), out.data_ptr(),
                                            ctypes.byref(ep), _stream()), "b200_conv_fprop")
     return out
@@ -125,7 +133,7 @@ def conv_dgrad(dy, wt, desc, out=None, residual=None):
     _chk(dy, bf16, "dy"); _chk(wt, bf16, "wt"); _chk(residual, bf16, "residual")
     if out is None:
         out = torch.empty((desc.N, desc.H, desc.W, desc.C), device=dy.device, dtype=bf16)
-    with _T('conv_dgrad', _conv_flops(desc), 0):
+    with _T('conv_dgrad', _conv_flops(desc), _conv_bytes(dy, wt, out, residual)):
         _l.check(_l.load().b200_conv_dgrad(ctypes.byref(desc), dy.data_ptr(), wt.data_ptr(), out.data_ptr(),
                                            _l.ptr(residual), _stream()), "b200_conv_dgrad")
     return out
@@ -147,7 +155,7 @@ def conv_wgrad(x, dy, desc, dw):
     """dw [K,R*S,C] fp32 += dy^T (*) x."""
     _chk(x, bf16, "x"); _chk(dy, bf16, "dy"); _chk(dw, torch.float32, "dw")
     ws = _wgrad_workspace(x.device)
-    with _T('conv_wgrad', _conv_flops(desc), 0):
+    with _T('conv_wgrad', _conv_flops(desc), _conv_bytes(x, dy, dw)):
         _l.check(_l.load().b200_conv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
                                            ws.data_ptr(), ws.numel(), _stream()), "b200_conv_wgrad")
     return dw
@@ -157,8 +165,9 @@ def dwconv_fprop(x, w, desc, out=None):
     _chk(x, bf16, "x"); _chk(w, bf16, "w")
     if out is None:
         out = torch.empty((desc.N, desc.P, desc.Q, desc.K), device=x.device, dtype=bf16)
-    _l.check(_l.load().b200_dwconv_fprop(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), out.data_ptr(), _stream()),
-             "b200_dwconv_fprop")
+    with _T('dw_fprop', 0, _conv_bytes(x, w, out)):       # HBM-bound class (name does not start with conv_)
+        _l.check(_l.load().b200_dwconv_fprop(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), out.data_ptr(), _stream()),
+                 "b200_dwconv_fprop")
     return out
 
 
@@ -166,15 +175,17 @@ def dwconv_dgrad(dy, w, desc, out=None):
     _chk(dy, bf16, "dy"); _chk(w, bf16, "w")
     if out is None:
         out = torch.empty((desc.N, desc.H, desc.W, desc.C), device=dy.device, dtype=bf16)
-    _l.check(_l.load().b200_dwconv_dgrad(ctypes.byref(desc), dy.data_ptr(), w.data_ptr(), out.data_ptr(), _stream()),
-             "b200_dwconv_dgrad")
+    with _T('dw_dgrad', 0, _conv_bytes(dy, w, out)):
+        _l.check(_l.load().b200_dwconv_dgrad(ctypes.byref(desc), dy.data_ptr(), w.data_ptr(), out.data_ptr(), _stream()),
+                 "b200_dwconv_dgrad")
     return out
 
 
 def dwconv_wgrad(x, dy, desc, dw, workspace):
     _chk(x, bf16, "x"); _chk(dy, bf16, "dy"); _chk(dw, torch.float32, "dw"); _chk(workspace, torch.float32, "ws")
-    _l.check(_l.load().b200_dwconv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
-                                         workspace.data_ptr(), workspace.numel() * 4, _stream()), "b200_dwconv_wgrad")
+    with _T('dw_wgrad', 0, _conv_bytes(x, dy, dw)):
+        _l.check(_l.load().b200_dwconv_wgrad(ctypes.byref(desc), x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                                             workspace.data_ptr(), workspace.numel() * 4, _stream()), "b200_dwconv_wgrad")
     return dw
 
 
@@ -507,7 +518,7 @@ def colsum_bf16(m, out):
 
 def fused_sgd(p32, g32, m32, p16, n, wd_count, lr, momentum, dampening, weight_decay, inv_scale, clip_coef,
               first_step, zero_grad=False):
-    with _T('fused_sgd', 0, (26 if zero_grad else 22) * int(n)):
+    with _T('fused_sgd', 0, (26 if zero_grad else 22) * int(n)):   # 12 B read + 10 B written (+4 B memset) per parameter
         _l.check(_l.load().b200_fused_sgd(p32.data_ptr(), g32.data_ptr(), _l.ptr(m32), _l.ptr(p16), int(n),
                                           int(wd_count), float(lr), float(momentum), float(dampening),
                                           float(weight_decay), float(inv_scale), _l.ptr(clip_coef), int(bool(first_step)),

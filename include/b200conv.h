@@ -223,7 +223,8 @@ int b200_colsum_bf16(const void* m, int B, int K, float* out, b200_stream_t stre
  * fp32->low-precision copy-back (utils/optim.py:43-47,263-264) in ONE pass over flat arenas.
  * Elements [0, wd_count) receive weight decay. hyper: device or host pointer is NOT used; values
  * are passed by value except clip_coef_dev (device scalar multiplied into g, may be NULL).
- * zero_grad != 0: g32 is cleared in the same pass (OptimRegime.zero_grad of the NEXT step, utils/optim.py:246-252). */
+ * zero_grad != 0: g32 is cleared by a memset behind the update, inside this call (OptimRegime.zero_grad of the NEXT step,
+ * utils/optim.py:246-252). */
 int b200_fused_sgd(float* p32, float* g32, float* m32, void* p16, long long n, long long wd_count,
                    float lr, float momentum, float dampening, float weight_decay, float inv_scale,
                    const float* clip_coef_dev, int first_step, int zero_grad, b200_stream_t stream);

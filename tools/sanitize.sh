@@ -7,7 +7,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 SEL='test_conv_fprop_dgrad_wgrad or test_fused_bn_statistics or test_bn_forward_backward or test_stem_bn_relu_maxpool_fused or test_grouped_conv_window_mode'
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 \
+  timeout 420 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 \
     python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "$SEL" > $OUT/${TAG}_sanitizer_$tool.full.log 2>&1
   echo "rc=$?" >> $OUT/${TAG}_sanitizer_$tool.full.log
   { echo "# compute-sanitizer --tool $tool, tests/test_gpu_ops.py -k \"$SEL\""; \
