@@ -136,7 +136,7 @@ def test_bn_cumulative_momentum():
     assert rel(rm.cpu(), bn.running_mean) < 1e-5 and rel(rv.cpu(), bn.running_var) < 1e-5
 
 
-@pytest.mark.parametrize("N,H,W,C", [(2, 112, 112, 64), (3, 17, 23, 16), (1, 8, 8, 8)])
+@pytest.mark.parametrize("N,H,W,C", [(2, 112, 112, 64), (3, 17, 23, 16), (1, 8, 8, 8), (5, 30, 31, 24), (70, 59, 8, 64)])
 def test_maxpool(N, H, W, C):
     ops = _ops()
     x = torch.randn(N, H, W, C).cuda().to(bf16)
