@@ -49,6 +49,10 @@ struct IgemmParams {
   int tma_store;         // 1: dense bf16 output staged in smem and written by TMA (tmC), residual via tmR
   int plain_a;           // 1: A is a dense [M_total, SC] matrix (1x1, stride 1, no padding): tiled TMA
   int b_stationary;      // 1: every (tap, k-block) weight slice stays in shared memory (small 1x1 layers): only A streams
+  int own_ntile;         // 1 (with b_stationary): the CTA owns n-tile blockIdx.x % n_tiles -- its weight slices are loaded
+                         // once -- and walks the m-tiles blockIdx.x / n_tiles, + gridDim.x / n_tiles, ... (the grid is a
+                         // multiple of n_tiles).  Cuts the L2->SM re-streaming of the weights from once per tile to once
+                         // per CTA for layers whose per-n-tile weights fit in shared memory (K <= 256 at N-tile 256)
   int epi_bufs;          // 1 or 2 output staging tiles: with 2 the residual tile of the NEXT tile is fetched while this one
                          // is converted and stored, and a store never waits for the previous one (write-heavy epilogues)
   uint32_t epi_bytes;
@@ -180,21 +184,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.ntaps * p.c_chunks;
+  // tile walk: round-robin over all (m, n) tiles, or -- owned n-tile -- over the m-tiles of one n-tile
+  const int walk_first = p.own_ntile ? static_cast<int>(blockIdx.x) / p.n_tiles : static_cast<int>(blockIdx.x);
+  const int walk_step = p.own_ntile ? static_cast<int>(gridDim.x) / p.n_tiles : static_cast<int>(gridDim.x);
+  const int walk_end = p.own_ntile ? p.m_tiles : total_tiles;
+  const int own_n = static_cast<int>(blockIdx.x) % p.n_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const int IJ = p.I * p.J;
-      if (p.b_stationary && blockIdx.x < total_tiles) {   // n_tiles == 1: the same slices serve every tile of the CTA
+      if (p.b_stationary && walk_first < walk_end) {   // the same slices serve every tile of the CTA
         mbar_arrive_expect_tx(&bstat_bar, static_cast<uint32_t>(k_iters) * (p.tx_bytes - p.a_bytes));
         for (int t = 0; t < p.ntaps; ++t)
           for (int cc = 0; cc < p.c_chunks; ++cc)
-            tma_load_3d(&tmB, &bstat_bar, sBstat + (t * p.c_chunks + cc) * p.b_bytes, cc * p.ck, p.taps[t].b_tap, 0);
+            tma_load_3d(&tmB, &bstat_bar, sBstat + (t * p.c_chunks + cc) * p.b_bytes, cc * p.ck, p.taps[t].b_tap,
+                        p.own_ntile ? own_n * p.block_n : 0);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile - m_tile * p.n_tiles;
+      for (int tile = walk_first; tile < walk_end; tile += walk_step) {
+        const int m_tile = p.own_ntile ? tile : tile / p.n_tiles;
+        const int n_tile = p.own_ntile ? own_n : tile - m_tile * p.n_tiles;
         const int m0 = m_tile * kTileM;
         const int img = m0 / IJ;
         const int rem = m0 - img * IJ;
@@ -230,13 +240,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // (bytes >> 4) instead of re-encoding it for every MMA.
       const uint64_t proto = make_smem_desc(0, 16, 8 * row_bytes, layout_type_for_row_bytes(row_bytes));
       const int ksteps = p.ck / 16;
-      if (p.b_stationary && blockIdx.x < total_tiles) {
+      if (p.b_stationary && walk_first < walk_end) {
         mbar_wait(&bstat_bar, 0);
         tc_fence_after();
       }
       const uint32_t bstat_addr = smem_u32(sBstat);
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int tile = walk_first; tile < walk_end; tile += walk_step, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1u;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -274,11 +284,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float st_s1 = 0.f, st_s2 = 0.f;
     const int IJ = p.I * p.J;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = walk_first; tile < walk_end; tile += walk_step, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1u;
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile - m_tile * p.n_tiles;
+      const int m_tile = p.own_ntile ? tile : tile / p.n_tiles;
+      const int n_tile = p.own_ntile ? own_n : tile - m_tile * p.n_tiles;
       const int m = m_tile * kTileM + q * 32 + lane;
       const bool row_ok = m < p.M_total;
       long long off = 0;
@@ -311,7 +321,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (p.res != nullptr) {
             auto fetch = [&](int t_tile, int buf) {
-              const int mt = t_tile / p.n_tiles, nt = t_tile - mt * p.n_tiles;
+              const int mt = p.own_ntile ? t_tile : t_tile / p.n_tiles;
+              const int nt = p.own_ntile ? own_n : t_tile - mt * p.n_tiles;
               uint8_t* dst = epi_base + buf * p.epi_bytes;
               mbar_arrive_expect_tx(&res_bar[buf], static_cast<uint32_t>(nbox) * kTileM * 128u);
               for (int b = 0; b < nbox; ++b)
@@ -319,8 +330,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             };
             if (p.epi_bufs == 2) {
               if (local == 0) fetch(tile, 0);
-              const int next = tile + static_cast<int>(gridDim.x);
-              if (next < total_tiles) fetch(next, eb ^ 1);      // lands while this tile is converted and stored
+              const int next = tile + walk_step;
+              if (next < walk_end) fetch(next, eb ^ 1);         // lands while this tile is converted and stored
             } else {
               fetch(tile, 0);
             }
@@ -814,6 +825,7 @@ static int encode_tiled2(CUtensorMap* tm, const void* base, int d0, long long d1
 }
 
 static const int kSmemBudget = 200 * 1024;
+static const int kSmemBudgetMax = 224 * 1024;   // owned-n-tile mode: resident weights + staging tile + >= 2 operand stages
 
 static int set_smem_attr(const void* fn, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -877,6 +889,29 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     bstat_bytes = b_all;
     stage = p.a_bytes;
   }
+  // several n-tiles whose weights fit one at a time: a CTA owns an n-tile.  Worth it when the weights dominate the
+  // L2->SM traffic of the round-robin walk (bytes ~ A * n_tiles + W * m_tiles vs A * n_tiles + W_tile * CTAs) and
+  // every CTA still gets a few m-tiles; needs >= 2 operand stages beside the resident weights and the staging tile.
+  static const int own_mode = getenv("B200_IGEMM_OWN_NTILE") ? atoi(getenv("B200_IGEMM_OWN_NTILE")) : 1;
+  int grid_own = 0;
+  int budget = kSmemBudget;
+  if (bstat_enabled && own_mode && !p.b_stationary && p.n_tiles > 1 && p.n_tiles <= 8 && !L.window &&
+      (p.a_bytes % 1024) == 0 && (p.b_bytes % 1024) == 0 && (L.Nout % p.block_n) == 0) {
+    const int ctas = sm_count() / p.n_tiles;
+    const long long a_all = (long long)p.M_total * L.SC * 2 * L.ntaps;
+    const long long w_all = (long long)b_all * p.n_tiles;
+    const long long rr_bytes = a_all * p.n_tiles + w_all * p.m_tiles;
+    const long long own_bytes = a_all * p.n_tiles + (long long)b_all * ctas * p.n_tiles;
+    const int stages_left = (kSmemBudgetMax - epi_bytes - b_all) / (int)p.a_bytes;
+    if (ctas >= 1 && p.m_tiles >= 4 * ctas && stages_left >= 2 && own_bytes * 4 <= rr_bytes * 3) {
+      p.b_stationary = 1;
+      p.own_ntile = 1;
+      bstat_bytes = b_all;
+      stage = p.a_bytes;
+      grid_own = ctas * p.n_tiles;
+      budget = kSmemBudgetMax;
+    }
+  }
   // second staging tile (residual prefetched one tile ahead, store/convert overlap) when at least three operand
   // stages remain.  B200_IGEMM_EPI2: 0 = never, 2 = every epilogue, default 1 = epilogues with a residual only --
   // measured (profiles/r02_summary.md): residual epilogues gain up to 28 %, plain ones lose 0-8 % to the lost stage
@@ -884,10 +919,10 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.epi_bufs = 1;
   p.epi_bytes = (uint32_t)epi_bytes;
   if ((epi2_mode >= 2 || (epi2_mode == 1 && L.res != nullptr)) && p.tma_store &&
-      (kSmemBudget - 2 * epi_bytes - bstat_bytes) / (int)stage >= 3)
+      (budget - 2 * epi_bytes - bstat_bytes) / (int)stage >= 3)
     p.epi_bufs = 2;
   const int epi_total = epi_bytes * p.epi_bufs;
-  p.num_stages = (kSmemBudget - epi_total - bstat_bytes) / (int)stage;
+  p.num_stages = (budget - epi_total - bstat_bytes) / (int)stage;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (p.num_stages < 2) p.num_stages = 2;
   p.OH = L.OH; p.OW = L.OW; p.os = L.os; p.oh0 = L.oh0; p.ow0 = L.ow0; p.ldo = L.ldo;
@@ -930,7 +965,11 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   rc = set_smem_attr((const void*)conv_igemm_kernel, smem_bytes);
   if (rc) return rc;
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+  const int grid = grid_own ? grid_own : (total_tiles < sm_count() ? total_tiles : sm_count());
+  if (getenv("B200_IGEMM_DEBUG"))
+    fprintf(stderr, "[igemm] M=%d C=%d N=%d taps=%d block_n=%d n_tiles=%d stages=%d bstat=%d own=%d epi_bufs=%d grid=%d smem=%d\n",
+            p.M_total, L.SC, L.Nout, L.ntaps, p.block_n, p.n_tiles, p.num_stages, p.b_stationary, p.own_ntile, p.epi_bufs,
+            grid, smem_bytes);
   b200::launch(conv_igemm_kernel, grid, kIgemmThreads, smem_bytes, stream, tmA, tmB, tmC, tmR, p);
   B200_CHECK_LAUNCH("conv_igemm_kernel");
   return B200_OK;

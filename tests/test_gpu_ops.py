@@ -392,7 +392,8 @@ def test_wide_pixel_stem_matches_7x7_conv():
     assert rel(dw, gw.permute(0, 2, 3, 1)) < 1e-4
 
 
-@pytest.mark.parametrize("N,H,C,K,R", [(4, 28, 64, 64, 3), (8, 14, 128, 256, 1), (3, 9, 64, 512, 1), (2, 56, 64, 128, 1)])
+@pytest.mark.parametrize("N,H,C,K,R", [(4, 28, 64, 64, 3), (8, 14, 128, 256, 1), (3, 9, 64, 512, 1), (2, 56, 64, 128, 1),
+                                       (97, 14, 256, 1024, 1), (50, 28, 128, 512, 1)])   # the last two: owned-n-tile walk
 def test_fused_bn_statistics_in_conv_epilogue(N, H, C, K, R):
     """conv_fprop(bn_stats_ws=...) + bn_finalize == conv_fprop followed by bn_stats on its output."""
     ops = _ops()
@@ -439,6 +440,8 @@ _CONV_CASE_NAMES = [
     # halo (shift-GEMM) path: 3x3 stride 1 at several map sizes / ragged last tile / residual epilogue / stem 4x4
     'halo_28_128', 'halo_14_256', 'halo_56_res', 'halo_36_odd', 'halo_18_512', 'halo_20x12', 'halo_56_128',
     'halo_8_256', 'halo_stem', 'halo_stem_67',
+    # owned-n-tile (weight-stationary) walk of the igemm kernel
+    'own_256_1024', 'own_1024_256', 'own_128_512_res',
 ]
 
 

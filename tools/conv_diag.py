@@ -49,6 +49,11 @@ CASES = {
     "p1_256_128_ragged": (3, 13, 13, 256, 128, 1, 1, 1, 0, {}),
     "p1_512_512_res": (2, 14, 14, 512, 512, 1, 1, 1, 0, {"residual": True, "act": 1}),
     "p1_256_1024_14": (4, 14, 14, 256, 1024, 1, 1, 1, 0, {}),
+    # enough m-tiles for the owned-n-tile (weight-stationary) walk of the igemm kernel: fprop with 4 n-tiles (ragged M),
+    # dgrad with 4 n-tiles, 2 n-tiles with residual + ReLU epilogue
+    "own_256_1024": (97, 14, 14, 256, 1024, 1, 1, 1, 0, {}),
+    "own_1024_256": (97, 14, 14, 1024, 256, 1, 1, 1, 0, {}),
+    "own_128_512_res": (50, 28, 28, 128, 512, 1, 1, 1, 0, {"residual": True, "act": 1}),
 }
 
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 call 1: full GPU suite (calibrates the survey bounds), ncu single-CTA vs CTA-pair on layer3/4 1x1, quick bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -s 2>&1 | grep -vE "^\s*$" | tail -150 > gpurun_out/r2_pytest1.log
 NCU="ncu --set full --clock-control none --import-source on -f"

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_engine.py tests/test_gpu_parity.py -m gpu -q -s -k "conv_fprop_dgrad or fused_bn or resnet50_imagenet_against or resnet20 or graph or full_size or grouped or mobilenet_v1 or eval_with_folded" > gpurun_out/r2_pytest10.log 2>&1
 grep -E "passed|failed|^FAILED|^E  " gpurun_out/r2_pytest10.log | cut -c1-300 | head -20

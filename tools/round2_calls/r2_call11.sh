@@ -1,7 +1,7 @@
 #!/bin/bash
 # 2-GPU validation: on-device DDP / SyncBN test, then the contract bench with the overlapped and the flat all-reduce;
 # wall time and exit code of every torchrun are logged (teardown must not hang).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/r2_multi11.log
 nvidia-smi --query-gpu=index,name --format=csv > $L 2>&1

@@ -1,7 +1,7 @@
 #!/bin/bash
 # programmatic dependent launch (B200_PDL), fused stem bn/relu/maxpool (B200_FUSE_STEM_POOL), high-priority main chain
 # (B200_MAIN_PRIORITY), row-quad activation masks (B200_BN_ACT_MASK): full GPU suite with PDL on, then one-at-a-time A/B
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 B200_PDL=1 timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/r2_pytest12.log 2>&1
 echo "pytest rc=$?"

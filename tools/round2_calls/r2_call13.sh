@@ -1,6 +1,6 @@
 #!/bin/bash
 # after the 32-bit index fix: op tests + MobileNet-v1, then A/B of stem fusion / priority / masks on the three models
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_engine.py -m gpu -q -s -k "bn_ or maxpool or stem or mobilenet_v1 or resnet50_imagenet or resnet18" > gpurun_out/r2_pytest13.log 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest13.log | cut -c1-300

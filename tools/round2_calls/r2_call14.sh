@@ -1,7 +1,7 @@
 #!/bin/bash
 # new defaults (row-quad masks, high-priority main chain, fused stem forward): full GPU suite, default bench, a few A/Bs,
 # then the round-2 profiling pass
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -s > gpurun_out/r2_pytest14.log 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest14.log | cut -c1-300

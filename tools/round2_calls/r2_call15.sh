@@ -1,7 +1,7 @@
 #!/bin/bash
 # sliding-window depthwise kernels: op tests + MobileNet parity, MobileNet-v2 bench A/B; fused-SGD microbenchmark;
 # compute-sanitizer pass
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_engine.py -m gpu -q -s -k "depthwise or mobilenet" > gpurun_out/r2_pytest15.log 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest15.log | cut -c1-300

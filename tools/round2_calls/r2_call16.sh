@@ -1,6 +1,6 @@
 #!/bin/bash
 # SGD clearing via memset, depthwise wgrad on the side stream: full GPU suite + benches of the three models
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -s > gpurun_out/r2_pytest16.log 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest16.log | cut -c1-300

@@ -1,6 +1,6 @@
 #!/bin/bash
 # sliding-window max pool + parallel depthwise-wgrad final reduce: op tests, engine tests, benches
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_engine.py -m gpu -q -s -k "maxpool or stem or depthwise or mobilenet or resnet50_imagenet or resnet18 or resnext50" > gpurun_out/r2_pytest17.log 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest17.log | cut -c1-300

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for v in A B C D; do timeout 120 python tools/capture_diag.py $v 2>&1 | grep CAPTURE; done > gpurun_out/r2_capture_diag.log
 cat gpurun_out/r2_capture_diag.log

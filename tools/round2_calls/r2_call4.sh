@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 L=gpurun_out/r2_wgrad_debug2.log; : > $L
 for lib in gpurun_tmp/old/libb200conv.so convnet/pytorch_b200/libb200conv.so; do
   for c in c3_64_64 c3s2_128_128_56 stem_s2d; do

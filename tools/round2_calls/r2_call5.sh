@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -s > gpurun_out/r2_pytest5.log 2>&1
 grep -E "^F?\.*T1|^F?\.*T2|T1 logits|T2 logits|MBv2|duplicates|adapt_grad|full-size|^   [a-z0-9.]+ +cos|uint8|evaluate:|passed|failed|^FAILED" gpurun_out/r2_pytest5.log | cut -c1-420

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 600 python tools/parity_diag.py 50 224 32 oracle > gpurun_out/r2_parity_50_224.log 2>&1
 timeout 600 python tools/parity_diag.py 50 64 32 oracle > gpurun_out/r2_parity_50_64.log 2>&1
 timeout 600 python tools/parity_diag.py 18 128 32 oracle > gpurun_out/r2_parity_18_128.log 2>&1

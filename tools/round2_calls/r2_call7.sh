@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q -s > gpurun_out/r2_pytest7.log 2>&1
 grep -E "T1 |T2 |MBv1|MBv2|duplicates|adapt_grad|full-size|^   [a-z0-9.]+ +cos|uint8|evaluate:|passed|failed|^FAILED|^E  " gpurun_out/r2_pytest7.log | cut -c1-520 | head -120

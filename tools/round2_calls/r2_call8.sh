@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for c in g32_128_56 g32_256_28s2 g32_512_14 g32_1024_7 g8_256_20x12; do timeout 90 python tools/conv_diag.py $c 2>&1 | grep DIAG | cut -c1-600; done > gpurun_out/r2_grouped_diag.log 2>&1
 cat gpurun_out/r2_grouped_diag.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/r2_multi.log 2>&1
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s >> gpurun_out/r2_multi.log 2>&1
