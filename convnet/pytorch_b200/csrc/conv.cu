@@ -825,7 +825,7 @@ static int encode_tiled2(CUtensorMap* tm, const void* base, int d0, long long d1
 }
 
 static const int kSmemBudget = 200 * 1024;
-static const int kSmemBudgetMax = 224 * 1024;   // owned-n-tile mode: resident weights + staging tile + >= 2 operand stages
+static const int kSmemBudgetMax = 224 * 1024;   // + 1 KB alignment slack + static barriers < the 227 KB per-CTA limit
 
 static int set_smem_attr(const void* fn, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -891,10 +891,14 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   }
   // several n-tiles whose weights fit one at a time: a CTA owns an n-tile.  Worth it when the weights dominate the
   // L2->SM traffic of the round-robin walk (bytes ~ A * n_tiles + W * m_tiles vs A * n_tiles + W_tile * CTAs) and
-  // every CTA still gets a few m-tiles; needs >= 2 operand stages beside the resident weights and the staging tile.
+  // every CTA still gets a few m-tiles; needs >= 3 operand stages beside the resident weights and the staging tile
+  // (with two, l3 256->1024 did not gain although its L2->SM traffic fell 2.5x: pipeline depth matters as much).
   static const int own_mode = getenv("B200_IGEMM_OWN_NTILE") ? atoi(getenv("B200_IGEMM_OWN_NTILE")) : 1;
   int grid_own = 0;
-  int budget = kSmemBudget;
+  // B200_IGEMM_SMEM_KB: operand + staging budget (default 224 KB: three 48 KB stages for 256-wide tiles beside the 64 KB
+  // staging tile; with 200 KB they ran a TWO-stage pipeline -- l3/l4 1x1 layers 15-20 % slower, 0.35 ms/step)
+  static const int budget_kb = getenv("B200_IGEMM_SMEM_KB") ? atoi(getenv("B200_IGEMM_SMEM_KB")) : 224;
+  int budget = (budget_kb >= 96 && budget_kb <= 224 ? budget_kb : 224) * 1024;
   if (bstat_enabled && own_mode && !p.b_stationary && p.n_tiles > 1 && p.n_tiles <= 8 && !L.window &&
       (p.a_bytes % 1024) == 0 && (p.b_bytes % 1024) == 0 && (L.Nout % p.block_n) == 0) {
     const int ctas = sm_count() / p.n_tiles;
@@ -903,7 +907,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     const long long rr_bytes = a_all * p.n_tiles + w_all * p.m_tiles;
     const long long own_bytes = a_all * p.n_tiles + (long long)b_all * ctas * p.n_tiles;
     const int stages_left = (kSmemBudgetMax - epi_bytes - b_all) / (int)p.a_bytes;
-    if (ctas >= 1 && p.m_tiles >= 4 * ctas && stages_left >= 2 && own_bytes * 4 <= rr_bytes * 3) {
+    if (ctas >= 1 && p.m_tiles >= 4 * ctas && stages_left >= 3 && own_bytes * 4 <= rr_bytes * 3) {
       p.b_stationary = 1;
       p.own_ntile = 1;
       bstat_bytes = b_all;
@@ -1185,6 +1189,8 @@ extern "C" int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const voi
   p.splits = (p.total_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
   p.stage_bytes = p.kt * (kTileM / p.ckA) * p.boxA_bytes + p.boxes_per_cta * p.boxB_bytes;
   p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
+  // 200 KB, not the full 224: the weight gradients run on the side stream BESIDE the main stream's BatchNorm kernels,
+  // whose reduce blocks need ~10 KB of shared memory on the same SM
   p.num_stages = kSmemBudget / (int)p.stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (p.num_stages < 2) p.num_stages = 2;
