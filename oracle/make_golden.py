@@ -72,10 +72,72 @@ def mobilenet_v2_fixture(ref_models, ref_trainer, ref_optim, ref_ce):
     print('mobilenet_v2 fixture written')
 
 
+NEIGHBOURS = [('resnext50', 'resnext', dict(dataset='imagenet', depth=50)),
+              ('resnet_se50', 'resnet_se', dict(dataset='imagenet', depth=50)),
+              ('resnext_se50', 'resnext_se', dict(dataset='imagenet', depth=50)),
+              ('mobilenet_v1', 'mobilenet', dict(dataset='imagenet')),
+              # the hot-path families themselves, in double precision (their fp32 fixtures above carry rounding noise)
+              ('resnet50', 'resnet', dict(dataset='imagenet', depth=50)),
+              ('resnet18', 'resnet', dict(dataset='imagenet', depth=18)),
+              ('mobilenet_v2', 'mobilenet_v2', dict(dataset='imagenet'))]
+
+
+def neighbours_fixture(ref_models, ref_ce):
+    """Grouped convolutions (ResNeXt), squeeze-excitation gates (resnet_se / resnext_se: one SEBlock shared by the
+    blocks of a stage) and MobileNet-v1 (depthwise with bias): one training-mode forward/backward of the UNMODIFIED
+    reference models on 8 x 3x96x96 inputs at default init (seed 123), run in DOUBLE precision (the fp32 runs of these
+    networks carry 1e-3 of rounding noise in the SE variants) -- logits, loss, every parameter-gradient norm,
+    running-statistics sums.  Pins oracle.ref_model's restatement of those families (tests/test_oracle_golden.py)."""
+    blob = {}
+    x, y = synth(8, (3, 96, 96), 1000, seed=7)
+    blob['x'], blob['y'] = x.numpy(), y.numpy()
+    crit = ref_ce.CrossEntropyLoss()
+    for name, factory, cfg in NEIGHBOURS:
+        torch.manual_seed(123)
+        model = getattr(ref_models, factory)(**cfg)
+        for mod in model.modules():                 # dropout draws depend on the dtype: switched off for this fixture
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        # leave the vacuous default state (last-BN gamma = 0 silences whole branches): deterministic non-zero affine
+        g = torch.Generator().manual_seed(99)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if p.dim() == 1 and ('bn' in n or n.split('.')[-2].isdigit() or 'downsample' in n) and n.endswith('weight'):
+                    p.copy_(0.5 + torch.rand(p.shape, generator=g))
+        init = {k: v.clone() for k, v in model.state_dict().items()}
+        model.double()                  # fp64: the comparison with the restatement is then free of rounding noise
+        model.train()
+        out = model(x.double())
+        loss = crit(out, y)
+        loss.backward()
+        seen, names, norms = set(), [], []
+        for n, p in model.named_parameters():          # named_parameters() lists a shared SE gate once
+            if id(p) in seen or p.grad is None:
+                continue
+            seen.add(id(p)); names.append(n); norms.append(float(p.grad.norm()))
+        stats = {k: float(v.double().sum()) for k, v in model.state_dict().items() if 'running_' in k}
+        blob[name + '/logits'] = out.detach().numpy()
+        blob[name + '/loss'] = np.float64(float(loss))
+        blob[name + '/grad_names'] = np.array(names)
+        blob[name + '/grad_norms'] = np.array(norms)
+        blob[name + '/stat_names'] = np.array(list(stats.keys()))
+        blob[name + '/stat_sums'] = np.array(list(stats.values()))
+        # the perturbed affine parameters (everything else is re-created from the seed by the test)
+        for k, v in init.items():
+            if v.dim() == 1 and v.is_floating_point() and 'running' not in k and k.endswith('weight'):
+                blob[name + '/affine/' + k] = v.numpy()
+        print(name, 'loss %.5f' % float(loss), '%d gradients' % len(names))
+    np.savez_compressed(os.path.join(OUT, 'neighbours.npz'), **blob)
+    print('neighbours fixture written')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref_models, ref_trainer, ref_optim, ref_ce = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'neighbours':     # regenerate only this fixture
+        neighbours_fixture(ref_models, ref_ce)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'mobilenet_v2':   # regenerate only this fixture
         mobilenet_v2_fixture(ref_models, ref_trainer, ref_optim, ref_ce)
         return
